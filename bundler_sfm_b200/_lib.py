@@ -1,0 +1,73 @@
+"""ctypes binding of libbsfm_b200.so (the C ABI declared in include/bsfm_b200.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "libbsfm_b200.so")
+
+
+def load_library():
+    """Load libbsfm_b200.so; fail loudly if it was not built (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryMissing(
+            f"{path} not found: build it with `make -C bundler_sfm_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "bundler_sfm_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    c = ctypes
+    u8p, i32p, i64p = c.POINTER(c.c_uint8), c.POINTER(c.c_int32), c.POINTER(c.c_int64)
+    lib.bsfm_last_error.restype = c.c_char_p
+    lib.bsfm_version.restype = c.c_char_p
+    lib.bsfm_kernel_launches.restype = c.c_int64
+    lib.bsfm_set_device.argtypes = [c.c_int]
+    lib.bsfm_match_pair.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_int, c.c_double, c.c_void_p, c.c_int]
+    lib.bsfm_match_pair.restype = c.c_int
+    lib.bsfm_keydb_create.argtypes = [c.c_void_p, c.c_void_p, c.c_int]
+    lib.bsfm_keydb_create.restype = c.c_void_p
+    lib.bsfm_keydb_create_dev.argtypes = [c.c_void_p, c.c_void_p, c.c_int]
+    lib.bsfm_keydb_create_dev.restype = c.c_void_p
+    lib.bsfm_keydb_destroy.argtypes = [c.c_void_p]
+    lib.bsfm_keydb_destroy.restype = None
+    lib.bsfm_match_num_pairs.argtypes = [c.c_int, c.c_int]
+    lib.bsfm_match_num_pairs.restype = c.c_int64
+    lib.bsfm_match_run.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_double]
+    lib.bsfm_match_run.restype = c.c_int64
+    lib.bsfm_match_fetch.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p, c.c_int64]
+    lib.bsfm_match_fetch.restype = c.c_int
+    lib.bsfm_match_result_dev.argtypes = [c.c_void_p, c.POINTER(c.c_void_p), i64p, c.POINTER(c.c_void_p), i64p]
+    lib.bsfm_match_result_dev.restype = c.c_int
+    lib.bsfm_match_shard_pairs.argtypes = [c.c_void_p]
+    lib.bsfm_match_shard_pairs.restype = c.c_int64
+    lib.bsfm_match_last_timing.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.POINTER(c.c_int)]
+    lib.bsfm_match_last_timing.restype = c.c_int
+    lib.bsfm_match_all_pairs.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_double,
+                                         c.c_void_p, c.c_int64, c.c_void_p, c.c_int64]
+    lib.bsfm_match_all_pairs.restype = c.c_int64
+    _LIB = lib
+    return lib
+
+
+def last_error():
+    return load_library().bsfm_last_error().decode()
+
+
+class BsfmError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc < 0:
+        raise BsfmError(f"{what} failed ({rc}): {last_error()}")
+    return rc

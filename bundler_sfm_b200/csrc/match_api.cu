@@ -1,0 +1,424 @@
+// match_api.cu -- host side of the MATCH path behind the C ABI of include/bsfm_b200.h.
+// Mirrors the loop structure of src/KeyMatchFull.cpp:105-151 (i ascending, j ascending inside the
+// window) and the MatchKeys contract of src/keys2a.cpp:347-424.  No CPU fallback.
+#include "common.h"
+#include "match_kernels.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace bsfm {
+namespace match {
+// kernels (match_kernels.cu)
+__global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, const int32_t *, uint8_t *, int32_t *, int64_t);
+__global__ void match_dp4a_kernel(MatchParams);
+__global__ void match_tc_kernel(MatchParams);
+__global__ void match_verify_kernel(MatchParams, int);
+__global__ void match_finalize_kernel(const uint32_t *, const int32_t *, int, const RunImage *, int, int,
+                                      const int32_t *, const int32_t *, int32_t *, int32_t *);
+}  // namespace match
+}  // namespace bsfm
+
+using namespace bsfm;
+using namespace bsfm::match;
+
+struct bsfm_keydb {
+    int N = 0;
+    int device = 0;
+    int num_sms = 0;
+    std::vector<int64_t> key_off;   // N+1
+    std::vector<int32_t> doff;      // N+1 device row offsets (multiples of 256)
+    int64_t drows = 0;
+    uint8_t *d_keys_sw = nullptr;
+    int32_t *d_norms = nullptr;
+    int32_t *d_tile_img = nullptr;
+    int32_t *d_img_doff = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // result of the last run
+    int64_t shard_pairs = 0;
+    int64_t total_matches = 0;
+    int32_t *d_pair_counts = nullptr;
+    int64_t pair_cap = 0;
+    int32_t *d_matches = nullptr;   // [match_cap][2]
+    int64_t match_cap = 0;
+    float ms[3] = {0, 0, 0};
+    int launches = 0;
+    // scratch reused across runs
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device, const int64_t *key_off, int N)
+{
+    int rc = require_device();
+    if (rc != BSFM_OK) return rc;
+    if (N < 0 || (N > 0 && (!key_off || key_off[0] != 0))) {
+        set_error("bsfm_keydb_create: bad arguments (N=%d)", N);
+        return BSFM_ERR_ARG;
+    }
+    db->N = N;
+    BSFM_CUDA_TRY(cudaGetDevice(&db->device));
+    cudaDeviceProp prop;
+    BSFM_CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
+    db->num_sms = prop.multiProcessorCount;
+    db->key_off.assign(key_off, key_off + N + 1);
+    db->doff.resize(N + 1);
+    int64_t r = 0;
+    for (int i = 0; i < N; i++) {
+        int64_t n = key_off[i + 1] - key_off[i];
+        if (n < 0) { set_error("bsfm_keydb_create: key_off not monotone at %d", i); return BSFM_ERR_ARG; }
+        db->doff[i] = (int32_t) r;
+        r += (n + IMG_PAD - 1) / IMG_PAD * IMG_PAD;
+        if (r > (int64_t) INT_MAX - 1024) { set_error("bsfm_keydb_create: more than 2^31 descriptor rows"); return BSFM_ERR_ARG; }
+    }
+    db->doff[N] = (int32_t) r;
+    db->drows = r + IMG_PAD;   // one spare padded tile so any 256-row read stays in bounds
+    const int64_t ntiles = db->drows / TILE_Q;
+    std::vector<int32_t> tile_img((size_t) ntiles, -1);
+    for (int i = 0; i < N; i++)
+        for (int64_t t = db->doff[i] / TILE_Q; t < db->doff[i + 1] / TILE_Q; t++) tile_img[(size_t) t] = i;
+
+    BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    for (int e = 0; e < 4; e++) BSFM_CUDA_TRY(cudaEventCreate(&db->ev[e]));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_keys_sw, (size_t) db->drows * DESC_BYTES));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_norms, (size_t) db->drows * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_tile_img, (size_t) ntiles * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_img_doff, (size_t) (N + 1) * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_tile_img, tile_img.data(), (size_t) ntiles * sizeof(int32_t), cudaMemcpyHostToDevice, db->stream));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_img_doff, db->doff.data(), (size_t) (N + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, db->stream));
+
+    const int64_t total_keys = key_off[N];
+    uint8_t *d_raw = nullptr;
+    int64_t *d_key_off = nullptr;
+    BSFM_CUDA_TRY(cudaMalloc(&d_key_off, (size_t) (N + 1) * sizeof(int64_t)));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_key_off, key_off, (size_t) (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, db->stream));
+    if (keys_on_device) {
+        d_raw = const_cast<uint8_t *>(keys);
+    } else if (total_keys > 0) {
+        BSFM_CUDA_TRY(cudaMalloc(&d_raw, (size_t) total_keys * DESC_BYTES));
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_raw, keys, (size_t) total_keys * DESC_BYTES, cudaMemcpyHostToDevice, db->stream));
+    }
+    {
+        const int warps_per_block = 8;
+        const int64_t blocks = (db->drows + warps_per_block - 1) / warps_per_block;
+        prep_kernel<<<(unsigned) blocks, warps_per_block * 32, 0, db->stream>>>(d_raw, d_key_off, db->d_img_doff, db->d_tile_img,
+                                                                                 db->d_keys_sw, db->d_norms, db->drows);
+        BSFM_KERNEL_CHECK();
+    }
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    if (!keys_on_device && d_raw) cudaFree(d_raw);
+    cudaFree(d_key_off);
+    return BSFM_OK;
+}
+
+static int start_image(int i, int window_radius) { return (window_radius > 0) ? std::max(i - window_radius, 0) : 0; }
+
+static int ensure_scratch(bsfm_keydb *db, size_t bytes)
+{
+    if (db->scratch_bytes >= bytes) return BSFM_OK;
+    if (db->scratch) cudaFree(db->scratch);
+    db->scratch = nullptr; db->scratch_bytes = 0;
+    BSFM_CUDA_TRY(cudaMalloc(&db->scratch, bytes));
+    db->scratch_bytes = bytes;
+    return BSFM_OK;
+}
+
+static int grow_matches(bsfm_keydb *db, int64_t need)
+{
+    if (db->match_cap >= need) return BSFM_OK;
+    int64_t cap = std::max<int64_t>(need, std::max<int64_t>(db->match_cap * 2, 1 << 16));
+    int32_t *p = nullptr;
+    BSFM_CUDA_TRY(cudaMalloc(&p, (size_t) cap * 2 * sizeof(int32_t)));
+    if (db->d_matches && db->total_matches > 0)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(p, db->d_matches, (size_t) db->total_matches * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, db->stream));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    if (db->d_matches) cudaFree(db->d_matches);
+    db->d_matches = p;
+    db->match_cap = cap;
+    return BSFM_OK;
+}
+
+static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int window_radius, double ratio)
+{
+    clear_error();
+    if (!db) { set_error("bsfm_match_run: null db"); return BSFM_ERR_ARG; }
+    if (img_begin < 0 || img_end > db->N || img_begin > img_end) {
+        set_error("bsfm_match_run: image range [%d,%d) outside [0,%d)", img_begin, img_end, db->N);
+        return BSFM_ERR_ARG;
+    }
+    BSFM_CUDA_TRY(cudaSetDevice(db->device));
+    const int kernel_sel = env_int("BSFM_MATCH_KERNEL", BSFM_MATCH_KERNEL_TC);
+    const long long launches0 = g_kernel_launches.load();
+
+    // ---- run tables: KeyMatchFull.cpp:105-123 ------------------------------------------------
+    std::vector<RunImage> run;
+    int64_t npairs = 0;
+    int64_t nunits = 0;
+    for (int i = img_begin; i < img_end; i++) {
+        const int s = start_image(i, window_radius);
+        const int64_t n_i = db->key_off[i + 1] - db->key_off[i];
+        const int units = (db->doff[i] - db->doff[s]) / TILE_Q;
+        if (n_i > 0 && units > 0) {
+            RunImage R;
+            R.img = i; R.n = (int32_t) n_i; R.db_row0 = db->doff[i];
+            R.ntiles_db = (db->doff[i + 1] - db->doff[i]) / TILE_DB;
+            R.atile0 = db->doff[s] / TILE_Q; R.start_img = s;
+            R.unit0 = (int32_t) nunits; R.nunits = units; R.pair0 = npairs;
+            if (nunits + units > (int64_t) INT_MAX / 2) { set_error("bsfm_match_run: shard too large (work units overflow)"); return BSFM_ERR_ARG; }
+            run.push_back(R);
+            nunits += units;
+        }
+        npairs += i - s;
+    }
+    db->shard_pairs = npairs;
+    db->total_matches = 0;
+    db->ms[0] = db->ms[1] = db->ms[2] = 0;
+
+    if (npairs > db->pair_cap) {
+        if (db->d_pair_counts) cudaFree(db->d_pair_counts);
+        db->d_pair_counts = nullptr; db->pair_cap = 0;
+        BSFM_CUDA_TRY(cudaMalloc(&db->d_pair_counts, (size_t) std::max<int64_t>(npairs, 1) * sizeof(int32_t)));
+        db->pair_cap = std::max<int64_t>(npairs, 1);
+    }
+    BSFM_CUDA_TRY(cudaEventRecord(db->ev[0], db->stream));
+    if (npairs > 0) BSFM_CUDA_TRY(cudaMemsetAsync(db->d_pair_counts, 0, (size_t) npairs * sizeof(int32_t), db->stream));
+    if (run.empty()) {
+        BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+        db->launches = 0;
+        return 0;
+    }
+
+    const int K = (int) run.size();
+    RunImage *d_run = nullptr;
+    BSFM_CUDA_TRY(cudaMalloc(&d_run, (size_t) K * sizeof(RunImage)));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_run, run.data(), (size_t) K * sizeof(RunImage), cudaMemcpyHostToDevice, db->stream));
+
+    // ---- chunked launches ---------------------------------------------------------------------
+    const int64_t chunk_slots = std::max(1, env_int("BSFM_MATCH_CHUNK_MSLOTS", 32)) * (int64_t) (1 << 20);
+    const int64_t chunk_units = std::max<int64_t>(1, chunk_slots / TILE_Q);
+    const int64_t max_units = std::min<int64_t>(chunk_units, nunits);
+    const int64_t cap = max_units * TILE_Q;   // worst case: every query row is a candidate / match
+
+    // scratch carve-up
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *) nullptr, (uint32_t *) nullptr,
+                                    (const int32_t *) nullptr, (int32_t *) nullptr, (int) std::min<int64_t>(cap, INT_MAX), 0, 32, db->stream);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t) 255; return o; };
+    const size_t o_cand = carve((size_t) cap * 6 * sizeof(int32_t));
+    const size_t o_slot_a = carve((size_t) cap * sizeof(uint32_t));
+    const size_t o_slot_b = carve((size_t) cap * sizeof(uint32_t));
+    const size_t o_idx_a = carve((size_t) cap * sizeof(int32_t));
+    const size_t o_idx_b = carve((size_t) cap * sizeof(int32_t));
+    const size_t o_cnt = carve(64);
+    const size_t o_cub = carve(cub_bytes);
+    int rc = ensure_scratch(db, off);
+    if (rc != BSFM_OK) { cudaFree(d_run); return rc; }
+    uint8_t *S = (uint8_t *) db->scratch;
+
+    MatchParams P;
+    P.keys_sw = db->d_keys_sw; P.norms = db->d_norms; P.run_imgs = d_run; P.num_run_imgs = K;
+    P.ratio_sq = ratio * ratio;
+    P.cand = (int32_t *) (S + o_cand); P.cand_cap = (int32_t) cap;
+    P.match_slot = (uint32_t *) (S + o_slot_a); P.match_idx2 = (int32_t *) (S + o_idx_a); P.match_cap = (int32_t) cap;
+    P.counters = (int32_t *) (S + o_cnt);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
+        attr_set = true;
+    }
+
+    float ms_search = 0.f;
+    for (int64_t u0 = 0; u0 < nunits; u0 += chunk_units) {
+        const int64_t u1 = std::min(nunits, u0 + chunk_units);
+        P.unit_begin = (int32_t) u0; P.unit_end = (int32_t) u1;
+        BSFM_CUDA_TRY(cudaMemsetAsync(P.counters, 0, 64, db->stream));
+        BSFM_CUDA_TRY(cudaEventRecord(db->ev[1], db->stream));
+        int32_t h_cnt[4] = {0, 0, 0, 0};
+        if (kernel_sel == BSFM_MATCH_KERNEL_DP4A) {
+            match_dp4a_kernel<<<(unsigned) (u1 - u0), 256, 0, db->stream>>>(P);
+            BSFM_KERNEL_CHECK();
+            BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
+        } else {
+            const int grid = (int) std::min<int64_t>(db->num_sms, u1 - u0);
+            match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
+            BSFM_KERNEL_CHECK();
+            BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
+            BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
+            BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+            if (h_cnt[2]) { set_error("bsfm_match_run: candidate buffer overflow (internal)"); cudaFree(d_run); return BSFM_ERR_CUDA; }
+            const int ncand = h_cnt[0];
+            if (ncand > 0) {
+                const int64_t threads = (int64_t) ncand * 32;
+                match_verify_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, db->stream>>>(P, ncand);
+                BSFM_KERNEL_CHECK();
+            }
+        }
+        BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
+        BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, db->ev[1], db->ev[2]);
+            ms_search += ms;
+        }
+        if (h_cnt[2]) { set_error("bsfm_match_run: match buffer overflow (internal)"); cudaFree(d_run); return BSFM_ERR_CUDA; }
+        const int nmatch = h_cnt[1];
+        if (nmatch > 0) {
+            rc = grow_matches(db, db->total_matches + nmatch);
+            if (rc != BSFM_OK) { cudaFree(d_run); return rc; }
+            size_t tb = cub_bytes;
+            int end_bit = 1;
+            while (end_bit < 32 && ((uint64_t) 1 << end_bit) < (uint64_t) (u1 - u0) * TILE_Q) end_bit++;
+            cub::DeviceRadixSort::SortPairs(S + o_cub, tb, (const uint32_t *) (S + o_slot_a), (uint32_t *) (S + o_slot_b),
+                                            (const int32_t *) (S + o_idx_a), (int32_t *) (S + o_idx_b), nmatch, 0, end_bit, db->stream);
+            count_launch(3);
+            BSFM_CUDA_TRY(cudaGetLastError());
+            match_finalize_kernel<<<(nmatch + 255) / 256, 256, 0, db->stream>>>((const uint32_t *) (S + o_slot_b), (const int32_t *) (S + o_idx_b),
+                                                                                nmatch, d_run, K, (int) u0, db->d_tile_img, db->d_img_doff,
+                                                                                db->d_matches + 2 * db->total_matches, db->d_pair_counts);
+            BSFM_KERNEL_CHECK();
+            db->total_matches += nmatch;
+        }
+    }
+    BSFM_CUDA_TRY(cudaEventRecord(db->ev[3], db->stream));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    cudaFree(d_run);
+    float ms_total = 0.f;
+    cudaEventElapsedTime(&ms_total, db->ev[0], db->ev[3]);
+    db->ms[0] = ms_search; db->ms[1] = ms_total - ms_search; db->ms[2] = ms_total;
+    db->launches = (int) (g_kernel_launches.load() - launches0);
+    return db->total_matches;
+}
+
+extern "C" {
+
+bsfm_keydb *bsfm_keydb_create(const uint8_t *keys, const int64_t *key_off, int num_images)
+{
+    clear_error();
+    bsfm_keydb *db = new bsfm_keydb();
+    if (keydb_build(db, keys, false, key_off, num_images) != BSFM_OK) { bsfm_keydb_destroy(db); return nullptr; }
+    return db;
+}
+
+bsfm_keydb *bsfm_keydb_create_dev(const uint8_t *keys_dev, const int64_t *key_off, int num_images)
+{
+    clear_error();
+    bsfm_keydb *db = new bsfm_keydb();
+    if (keydb_build(db, keys_dev, true, key_off, num_images) != BSFM_OK) { bsfm_keydb_destroy(db); return nullptr; }
+    return db;
+}
+
+void bsfm_keydb_destroy(bsfm_keydb *db)
+{
+    if (!db) return;
+    cudaFree(db->d_keys_sw); cudaFree(db->d_norms); cudaFree(db->d_tile_img); cudaFree(db->d_img_doff);
+    cudaFree(db->d_pair_counts); cudaFree(db->d_matches); cudaFree(db->scratch);
+    for (int e = 0; e < 4; e++) if (db->ev[e]) cudaEventDestroy(db->ev[e]);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+int64_t bsfm_match_num_pairs(int num_images, int window_radius)
+{
+    int64_t p = 0;
+    for (int i = 0; i < num_images; i++) p += i - start_image(i, window_radius);
+    return p;
+}
+
+int64_t bsfm_match_run(bsfm_keydb *db, int img_begin, int img_end, int window_radius, double ratio)
+{
+    return match_run_impl(db, img_begin, img_end, window_radius, ratio);
+}
+
+int64_t bsfm_match_shard_pairs(bsfm_keydb *db) { return db ? db->shard_pairs : BSFM_ERR_ARG; }
+
+int bsfm_match_fetch(bsfm_keydb *db, int32_t *pair_counts, int64_t pair_cap, int32_t *matches, int64_t match_cap)
+{
+    clear_error();
+    if (!db) { set_error("bsfm_match_fetch: null db"); return BSFM_ERR_ARG; }
+    if (pair_cap < db->shard_pairs || match_cap < db->total_matches) {
+        set_error("bsfm_match_fetch: need %lld pairs / %lld matches, got %lld / %lld", (long long) db->shard_pairs,
+                  (long long) db->total_matches, (long long) pair_cap, (long long) match_cap);
+        return BSFM_ERR_CAPACITY;
+    }
+    if (db->shard_pairs > 0)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(pair_counts, db->d_pair_counts, (size_t) db->shard_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, db->stream));
+    if (db->total_matches > 0)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(matches, db->d_matches, (size_t) db->total_matches * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, db->stream));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    return BSFM_OK;
+}
+
+int bsfm_match_result_dev(bsfm_keydb *db, const int32_t **pair_counts_dev, int64_t *num_pairs,
+                          const int32_t **matches_dev, int64_t *num_matches)
+{
+    if (!db) { set_error("bsfm_match_result_dev: null db"); return BSFM_ERR_ARG; }
+    if (pair_counts_dev) *pair_counts_dev = db->d_pair_counts;
+    if (num_pairs) *num_pairs = db->shard_pairs;
+    if (matches_dev) *matches_dev = db->d_matches;
+    if (num_matches) *num_matches = db->total_matches;
+    return BSFM_OK;
+}
+
+int bsfm_match_last_timing(bsfm_keydb *db, float ms[3], int *launches)
+{
+    if (!db) { set_error("bsfm_match_last_timing: null db"); return BSFM_ERR_ARG; }
+    if (ms) { ms[0] = db->ms[0]; ms[1] = db->ms[1]; ms[2] = db->ms[2]; }
+    if (launches) *launches = db->launches;
+    return BSFM_OK;
+}
+
+int64_t bsfm_match_all_pairs(const uint8_t *keys, const int64_t *key_off, int num_images, int window_radius, double ratio,
+                             int32_t *pair_counts, int64_t pair_cap, int32_t *matches, int64_t match_cap)
+{
+    bsfm_keydb *db = bsfm_keydb_create(keys, key_off, num_images);
+    if (!db) return BSFM_ERR_CUDA;
+    int64_t total = bsfm_match_run(db, 0, num_images, window_radius, ratio);
+    if (total >= 0) {
+        int rc = bsfm_match_fetch(db, pair_counts, pair_cap, matches, match_cap);
+        if (rc != BSFM_OK) total = rc;
+    }
+    bsfm_keydb_destroy(db);
+    return total;
+}
+
+/* MatchKeys(k1 = queries, k2 = database): image 0 = k1, image 1 = k2, the single pair (0,1). */
+int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int32_t *out_pairs, int cap)
+{
+    clear_error();
+    if (n1 < 0 || n2 < 0 || cap < 0) { set_error("bsfm_match_pair: negative size"); return BSFM_ERR_ARG; }
+    int rc = require_device();
+    if (rc != BSFM_OK) return rc;
+    if (n1 == 0 || n2 == 0) return 0;
+    std::vector<uint8_t> keys((size_t) (n1 + n2) * DESC_BYTES);
+    memcpy(keys.data(), k1, (size_t) n1 * DESC_BYTES);
+    memcpy(keys.data() + (size_t) n1 * DESC_BYTES, k2, (size_t) n2 * DESC_BYTES);
+    int64_t off[3] = {0, n1, (int64_t) n1 + n2};
+    bsfm_keydb *db = bsfm_keydb_create(keys.data(), off, 2);
+    if (!db) return BSFM_ERR_CUDA;
+    int64_t total = bsfm_match_run(db, 1, 2, -1, ratio);
+    if (total > 0) {
+        std::vector<int32_t> m((size_t) total * 2);
+        int32_t pc = 0;
+        rc = bsfm_match_fetch(db, &pc, 1, m.data(), total);
+        if (rc != BSFM_OK) { bsfm_keydb_destroy(db); return rc; }
+        int64_t ncopy = std::min<int64_t>(total, cap);
+        if (ncopy > 0 && out_pairs) memcpy(out_pairs, m.data(), (size_t) ncopy * 2 * sizeof(int32_t));
+    }
+    bsfm_keydb_destroy(db);
+    if (total > INT_MAX) total = INT_MAX;
+    return (int) total;
+}
+
+}  // extern "C"

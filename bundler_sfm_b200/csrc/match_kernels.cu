@@ -1,0 +1,521 @@
+// match_kernels.cu -- sm_100a kernels of the MATCH hot path.  See match_kernels.cuh for layout.
+#include "match_kernels.cuh"
+#include <climits>
+
+namespace bsfm {
+namespace match {
+
+// ---------------------------------------------------------------------------------------------
+// prep: raw host-order descriptors (n_i x 128 per image, concatenated) -> padded swizzled layout
+// + squared norms.  One warp per device row; lane l handles bytes [4l, 4l+4).
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_kernel(const uint8_t *__restrict__ raw, const int64_t *__restrict__ key_off,
+                            const int32_t *__restrict__ img_doff, const int32_t *__restrict__ tile_img,
+                            uint8_t *__restrict__ keys_sw, int32_t *__restrict__ norms, int64_t drows)
+{
+    int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= drows) return;
+    int img = tile_img[row >> 7];
+    uint32_t w = 0;
+    int32_t nrm = NORM_PAD;
+    if (img >= 0) {
+        int64_t k = row - img_doff[img];
+        int64_t n = key_off[img + 1] - key_off[img];
+        if (k < n) {
+            const uint8_t *src = raw + (key_off[img] + k) * DESC_BYTES + lane * 4;
+            w = (uint32_t) src[0] | ((uint32_t) src[1] << 8) | ((uint32_t) src[2] << 16) | ((uint32_t) src[3] << 24);
+            uint32_t s = __dp4a(w, w, 0u);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            nrm = (int32_t) s;
+        }
+    }
+    int c = lane >> 2;  // 16-byte chunk
+    uint32_t *dst = reinterpret_cast<uint32_t *>(keys_sw + sw_chunk_offset(row, c)) + (lane & 3);
+    *dst = w;
+    if (lane == 0) norms[row] = nrm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DP4A kernel: one CTA per work unit (128 query rows x whole database image).  CUDA-core second
+// implementation used to cross-check the tensor-core kernel at full size and as the selectable
+// BSFM_MATCH_KERNEL_DP4A path.  Exact top-2 with index per row; emits final matches directly.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void top2_insert(int &m1, int &m2, int &mi, int t, int idx)
+{
+    // keeps (m1 <= m2); first-seen wins ties (pr_queue_k.h:102-117 strict '>')
+    if (t < m1) { m2 = m1; m1 = t; mi = idx; }
+    else if (t < m2) { m2 = t; }
+}
+
+__global__ void __launch_bounds__(256) match_dp4a_kernel(MatchParams P)
+{
+    __shared__ uint32_t sQ[32][TILE_Q];
+    __shared__ uint32_t sD[32][128];
+    __shared__ int32_t sN[128];
+
+    const int u = P.unit_begin + blockIdx.x;
+    if (u >= P.unit_end) return;
+    const int k = find_run_image(P.run_imgs, P.num_run_imgs, u);
+    const RunImage R = P.run_imgs[k];
+    const int64_t a_row0 = (int64_t) (R.atile0 + (u - R.unit0)) * TILE_Q;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    // query tile -> sQ[k4][row]
+    for (int idx = tid; idx < TILE_Q * 8; idx += 256) {
+        int c = idx >> 7, row = idx & 127;
+        uint4 v = *reinterpret_cast<const uint4 *>(P.keys_sw + sw_chunk_offset(a_row0 + row, c));
+        sQ[c * 4 + 0][row] = v.x; sQ[c * 4 + 1][row] = v.y; sQ[c * 4 + 2][row] = v.z; sQ[c * 4 + 3][row] = v.w;
+    }
+
+    int m1[8], m2[8], mi[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) { m1[a] = INT_MAX; m2[a] = INT_MAX; mi[a] = -1; }
+
+    const int ntiles = R.ntiles_db * 2;  // 128-row database tiles
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int64_t d_row0 = (int64_t) R.db_row0 + (int64_t) tile * 128;
+        __syncthreads();
+        for (int idx = tid; idx < 128 * 8; idx += 256) {
+            int c = idx >> 7, row = idx & 127;
+            uint4 v = *reinterpret_cast<const uint4 *>(P.keys_sw + sw_chunk_offset(d_row0 + row, c));
+            sD[c * 4 + 0][row] = v.x; sD[c * 4 + 1][row] = v.y; sD[c * 4 + 2][row] = v.z; sD[c * 4 + 3][row] = v.w;
+        }
+        if (tid < 128) sN[tid] = P.norms[d_row0 + tid];
+        __syncthreads();
+
+        uint32_t acc[8][8];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 8; b++) acc[a][b] = 0;
+#pragma unroll 4
+        for (int k4 = 0; k4 < 32; k4++) {
+            uint32_t q[8], d[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) q[a] = sQ[k4][ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 8; b++) d[b] = sD[k4][tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 8; b++) acc[a][b] = __dp4a(q[a], d[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int col = tile * 128 + tx + 16 * b;
+            const int nb = sN[tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                int t = nb - 2 * (int) acc[a][b];
+                top2_insert(m1[a], m2[a], mi[a], t, col);
+            }
+        }
+    }
+
+    // merge the 16 column-threads of every row (lanes differing in the low 4 bits)
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            int o1 = __shfl_xor_sync(0xffffffffu, m1[a], o);
+            int o2 = __shfl_xor_sync(0xffffffffu, m2[a], o);
+            int oi = __shfl_xor_sync(0xffffffffu, mi[a], o);
+            int hi = max(m1[a], o1);
+            int lo2 = min(m2[a], o2);
+            if (o1 < m1[a]) mi[a] = oi;
+            m1[a] = min(m1[a], o1);
+            m2[a] = min(hi, lo2);
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int r = ty + 16 * a;
+            const int na = P.norms[a_row0 + r];
+            if (na >= NORM_PAD_HALF) continue;  // padding query row
+            const int d0 = na + m1[a];
+            const int d1 = (m2[a] >= NORM_PAD_HALF) ? INT_MAX : na + m2[a];
+            if ((double) d0 < P.ratio_sq * (double) d1) {
+                int pos = atomicAdd(&P.counters[1], 1);
+                if (pos < P.match_cap) {
+                    P.match_slot[pos] = (uint32_t) (u - P.unit_begin) * TILE_Q + r;
+                    P.match_idx2[pos] = mi[a];
+                } else {
+                    P.counters[2] = 1;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 kernel: persistent, warp-specialised.
+//   warp 0      : TMA producer (cp.async.bulk, one 16 KB query tile per unit, 32 KB database tiles)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::i8, M128 N256 K32 x4)
+//   warps 2..5  : epilogue, one TMEM lane quadrant each (thread == query row)
+// Accumulators double-buffered in TMEM (2 x 256 columns); shared-memory database ring of 4 stages.
+// Epilogue per element: t = |p|^2 - 2*dot (IMAD), chunk minimum (VIMNMX3 tree).  Per 32-column
+// chunk the row keeps (m1 = smallest chunk-min, s2 = second smallest chunk-min, bchunk).  d0 is
+// exact; d1 is bounded above by s2, so only rows passing the ratio test with that bound can match:
+// they are pushed as candidates and resolved exactly by match_verify_kernel.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute
+// UMMA::SmemDescriptor bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout_type=SWIZZLE_128B(2) [61,64))
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t) 1 << 16;
+    d |= (uint64_t) (1024 >> 4) << 32;
+    d |= (uint64_t) 1 << 46;
+    d |= (uint64_t) 2 << 61;
+    return d;
+}
+// UMMA instruction descriptor (cute UMMA::InstrDescriptor): c_format S32(2) [4,6), a/b format
+// UINT8(0) [7,10)/[10,13), a/b K-major(0) [15],[16], N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t) (TILE_DB >> 3) << 17) | ((uint32_t) (TILE_Q >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct UnitInfo {
+    int64_t a_row0;
+    int32_t db_row0, n, ntiles_db;
+};
+__device__ __forceinline__ UnitInfo decode_unit(const MatchParams &P, int u)
+{
+    const int k = find_run_image(P.run_imgs, P.num_run_imgs, u);
+    const RunImage *R = P.run_imgs + k;
+    UnitInfo U;
+    U.a_row0 = (int64_t) (R->atile0 + (u - R->unit0)) * TILE_Q;
+    U.db_row0 = R->db_row0;
+    U.n = R->n;
+    U.ntiles_db = R->ntiles_db;
+    return U;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // manual 1024-byte alignment (SWIZZLE_128B atoms)
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw_addr);
+
+    const uint32_t sA = base + TC_SMEM_A;
+    const uint32_t sB = base + TC_SMEM_B;
+    int32_t *sN = reinterpret_cast<int32_t *>(smem + TC_SMEM_N);
+    const uint32_t bar0 = base + TC_SMEM_BAR;
+    // barrier map (8 bytes each)
+    const uint32_t bar_b_full = bar0;                          // [TC_B_STAGES]
+    const uint32_t bar_b_empty = bar0 + 8 * TC_B_STAGES;       // [TC_B_STAGES]
+    const uint32_t bar_a_full = bar0 + 16 * TC_B_STAGES;       // [2]
+    const uint32_t bar_a_empty = bar_a_full + 16;              // [2]
+    const uint32_t bar_t_full = bar_a_empty + 16;              // [2]
+    const uint32_t bar_t_empty = bar_t_full + 16;              // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_SMEM_BAR + 8 * (2 * TC_B_STAGES + 8));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_B_STAGES; s++) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_a_full + 8 * s, 1);
+            mbar_init(bar_a_empty + 8 * s, 1);
+            mbar_init(bar_t_full + 8 * s, 1);
+            mbar_init(bar_t_empty + 8 * s, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int u_first = P.unit_begin + blockIdx.x;
+    const int u_step = gridDim.x;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t bs = 0, bph = 0, as = 0, aph = 0;
+            for (int u = u_first; u < P.unit_end; u += u_step) {
+                const UnitInfo U = decode_unit(P, u);
+                mbar_wait(bar_a_empty + 8 * as, aph ^ 1);
+                mbar_expect_tx(bar_a_full + 8 * as, TC_A_BYTES);
+                tma_bulk_g2s(sA + as * TC_A_BYTES, P.keys_sw + (size_t) U.a_row0 * DESC_BYTES, TC_A_BYTES, bar_a_full + 8 * as);
+                as ^= 1; if (as == 0) aph ^= 1;
+                const uint8_t *src = P.keys_sw + (size_t) U.db_row0 * DESC_BYTES;
+                for (int t = 0; t < U.ntiles_db; t++) {
+                    mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+                    mbar_expect_tx(bar_b_full + 8 * bs, TC_B_BYTES);
+                    tma_bulk_g2s(sB + bs * TC_B_BYTES, src + (size_t) t * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * bs);
+                    if (++bs == TC_B_STAGES) { bs = 0; bph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t bs = 0, bph = 0, as = 0, aph = 0, ts = 0, tph = 0;
+            for (int u = u_first; u < P.unit_end; u += u_step) {
+                const UnitInfo U = decode_unit(P, u);
+                mbar_wait(bar_a_full + 8 * as, aph);
+                const uint64_t adesc = make_sw128_desc(sA + as * TC_A_BYTES);
+                for (int t = 0; t < U.ntiles_db; t++) {
+                    mbar_wait(bar_b_full + 8 * bs, bph);
+                    mbar_wait(bar_t_empty + 8 * ts, tph ^ 1);
+                    tc_fence_after();
+                    const uint64_t bdesc = make_sw128_desc(sB + bs * TC_B_BYTES);
+                    const uint32_t tmem_d = tmem_base + ts * TILE_DB;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)   // K = 4 x 32 bytes; +32 B = +2 in the descriptor start field
+                        tc_mma_i8(tmem_d, adesc + (uint64_t) (kk * 2), bdesc + (uint64_t) (kk * 2), TC_IDESC, kk > 0);
+                    tc_commit(bar_b_empty + 8 * bs);
+                    tc_commit(bar_t_full + 8 * ts);
+                    if (++bs == TC_B_STAGES) { bs = 0; bph ^= 1; }
+                    ts ^= 1; if (ts == 0) tph ^= 1;
+                }
+                tc_commit(bar_a_empty + 8 * as);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps) =====================
+        const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;        // query row inside the unit
+        const int etid = threadIdx.x - 64;       // 0..127
+        uint32_t ts = 0, tph = 0;
+        for (int u = u_first; u < P.unit_end; u += u_step) {
+            const UnitInfo U = decode_unit(P, u);
+            const int na = P.norms[U.a_row0 + row];
+            int m1 = INT_MAX, s2 = INT_MAX, bchunk = 0;
+            for (int t = 0; t < U.ntiles_db; t++) {
+                // stage this tile's 256 database norms in shared memory (buffer = accumulator stage)
+                const int2 nv = *reinterpret_cast<const int2 *>(P.norms + (size_t) U.db_row0 + (size_t) t * TILE_DB + etid * 2);
+                *reinterpret_cast<int2 *>(sN + ts * TILE_DB + etid * 2) = nv;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(bar_t_full + 8 * ts, tph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + ts * TILE_DB;
+                const int4 *nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB);
+#pragma unroll 1
+                for (int c = 0; c < TILE_DB / CHUNK; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * CHUNK, v);
+                    tmem_ld_wait();
+                    int cm = INT_MAX;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int4 nb = nb4[c * 8 + q];
+                        const int t0 = nb.x - 2 * (int) v[4 * q + 0];
+                        const int t1 = nb.y - 2 * (int) v[4 * q + 1];
+                        const int t2 = nb.z - 2 * (int) v[4 * q + 2];
+                        const int t3 = nb.w - 2 * (int) v[4 * q + 3];
+                        cm = min(cm, min(min(t0, t1), min(t2, t3)));
+                    }
+                    // (m1, s2) <- two smallest of {m1, s2, cm}
+                    const int hi = max(m1, cm);
+                    if (cm < m1) bchunk = t * (TILE_DB / CHUNK) + c;
+                    m1 = min(m1, cm);
+                    s2 = min(s2, hi);
+                }
+                tc_fence_before();
+                mbar_arrive(bar_t_empty + 8 * ts);
+                ts ^= 1; if (ts == 0) tph ^= 1;
+            }
+            // unit finished: provisional ratio test with the upper bound on d1
+            bool cand = false;
+            int d1u = INT_MAX;
+            if (na < NORM_PAD_HALF) {
+                const int d0 = na + m1;
+                d1u = (s2 >= NORM_PAD_HALF) ? INT_MAX : na + s2;
+                cand = (double) d0 < P.ratio_sq * (double) d1u;
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, cand);
+            if (ball) {
+                int basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&P.counters[0], __popc(ball));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (cand) {
+                    const int pos = basepos + __popc(ball & ((1u << lane) - 1u));
+                    if (pos < P.cand_cap) {
+                        const int col0 = bchunk * CHUNK;
+                        const size_t cap = (size_t) P.cand_cap;
+                        P.cand[0 * cap + pos] = (u - P.unit_begin) * TILE_Q + row;
+                        P.cand[1 * cap + pos] = (int32_t) (U.a_row0 + row);
+                        P.cand[2 * cap + pos] = U.db_row0 + col0;
+                        P.cand[3 * cap + pos] = col0;
+                        P.cand[4 * cap + pos] = min(CHUNK, U.n - col0);
+                        P.cand[5 * cap + pos] = d1u;
+                    } else {
+                        P.counters[2] = 1;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// verify: one warp per candidate.  Recomputes the 32 distances of the winning chunk with the
+// DEFINITION (sum of squared differences, kd_pr_search.cpp:200-209), finds the exact nearest
+// column and the chunk's own second minimum, applies the final ratio test.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sqdist_rows(const uint8_t *keys_sw, int64_t ra, int64_t rb)
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(keys_sw + sw_chunk_offset(ra, c));
+        const uint4 b = *reinterpret_cast<const uint4 *>(keys_sw + sw_chunk_offset(rb, c));
+        uint32_t dx = __vabsdiffu4(a.x, b.x), dy = __vabsdiffu4(a.y, b.y), dz = __vabsdiffu4(a.z, b.z), dw = __vabsdiffu4(a.w, b.w);
+        acc = __dp4a(dx, dx, acc); acc = __dp4a(dy, dy, acc); acc = __dp4a(dz, dz, acc); acc = __dp4a(dw, dw, acc);
+    }
+    return (int) acc;
+}
+
+__global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int ncand)
+{
+    const int w = (int) (((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= ncand) return;
+    const size_t cap = (size_t) P.cand_cap;
+    const int slot = P.cand[0 * cap + w];
+    const int qrow = P.cand[1 * cap + w];
+    const int db0 = P.cand[2 * cap + w];
+    const int col0 = P.cand[3 * cap + w];
+    const int nvalid = P.cand[4 * cap + w];
+    const int d1u = P.cand[5 * cap + w];
+
+    int d = INT_MAX;
+    if (lane < nvalid) d = sqdist_rows(P.keys_sw, qrow, (int64_t) db0 + lane);
+    // warp top-2 (value, lane)
+    int m1 = d, m2 = INT_MAX, mi = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int o1 = __shfl_xor_sync(0xffffffffu, m1, o);
+        int o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        int hi = max(m1, o1);
+        int lo2 = min(m2, o2);
+        if (o1 < m1 || (o1 == m1 && oi < mi)) mi = oi;
+        m1 = min(m1, o1);
+        m2 = min(hi, lo2);
+    }
+    if (lane == 0) {
+        const int d0 = m1;
+        const int d1 = min(d1u, m2);
+        if ((double) d0 < P.ratio_sq * (double) d1) {
+            int pos = atomicAdd(&P.counters[1], 1);
+            if (pos < P.match_cap) {
+                P.match_slot[pos] = (uint32_t) slot;
+                P.match_idx2[pos] = col0 + mi;
+            } else {
+                P.counters[2] = 1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: sorted (slot, idx2) -> (idx1, idx2) records + per-pair counts.
+// ---------------------------------------------------------------------------------------------
+__global__ void match_finalize_kernel(const uint32_t *__restrict__ slots, const int32_t *__restrict__ idx2,
+                                      int nmatch, const RunImage *__restrict__ run_imgs, int K, int unit_begin,
+                                      const int32_t *__restrict__ tile_img, const int32_t *__restrict__ img_doff,
+                                      int32_t *__restrict__ out_pairs /* [nmatch][2] */,
+                                      int32_t *__restrict__ pair_counts)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nmatch) return;
+    const uint32_t slot = slots[e];
+    const int u = unit_begin + (int) (slot >> 7);
+    const int r = (int) (slot & 127u);
+    const int k = find_run_image(run_imgs, K, u);
+    const RunImage R = run_imgs[k];
+    const int atile = R.atile0 + (u - R.unit0);
+    const int j = tile_img[atile];
+    const int idx1 = atile * TILE_Q + r - img_doff[j];
+    out_pairs[2 * (size_t) e + 0] = idx1;
+    out_pairs[2 * (size_t) e + 1] = idx2[e];
+    atomicAdd(&pair_counts[R.pair0 + (j - R.start_img)], 1);
+}
+
+}  // namespace match
+}  // namespace bsfm

@@ -1,0 +1,94 @@
+// match_kernels.cuh -- sm_100a kernels of the MATCH hot path.
+//
+// Reference semantics (file:line under /root/reference):
+//   for each query key q of image j and database image i (j < i):
+//     d(q,p) = sum_k ((int)q_k - (int)p_k)^2        lib/ann_1.1_char/src/kd_pr_search.cpp:200-209
+//     (d0, nn0), d1 = two smallest over p in image i lib/ann_1.1_char/src/pr_queue_k.h:102-117
+//     emit (q, nn0) iff (double)d0 < ratio*ratio*(double)d1        src/keys2a.cpp:362
+//
+// HBM layout: every image is padded to a multiple of 256 descriptor rows; a row is
+// 128 bytes; rows are stored in the UMMA "K-major, SWIZZLE_128B" canonical shared-memory image
+// (8-row x 128-byte atoms, 16-byte chunk c of row r stored at chunk c ^ (r & 7)) so that a tile
+// of rows is ONE contiguous TMA bulk copy and lands in shared memory ready for tcgen05.mma.
+// norms[row] = |p|^2 (int32) for real rows, NORM_PAD (2^30) for padding rows.
+//
+// d = |q|^2 + |p|^2 - 2 q.p is exact in int32 (max 128*255^2 = 8,323,200).  The tensor core
+// produces q.p (u8 x u8 -> s32, tcgen05.mma kind::i8); ranking uses t = |p|^2 - 2 q.p.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace bsfm {
+namespace match {
+
+constexpr int DESC_BYTES = 128;
+constexpr int TILE_Q = 128;          // query rows per work unit (= TMEM lanes = UMMA_M)
+constexpr int TILE_DB = 256;         // database rows per MMA tile (= UMMA_N)
+constexpr int IMG_PAD = 256;         // per-image row padding
+constexpr int CHUNK = 32;            // database columns per epilogue chunk (one tcgen05.ld.x32)
+constexpr int32_t NORM_PAD = 1 << 30;
+constexpr int32_t NORM_PAD_HALF = 1 << 29;
+
+// tensor-core kernel configuration (shared by kernel and launcher)
+constexpr int TC_THREADS = 192;
+constexpr int TC_B_STAGES = 4;
+constexpr int TC_A_BYTES = TILE_Q * DESC_BYTES;    // 16384
+constexpr int TC_B_BYTES = TILE_DB * DESC_BYTES;   // 32768
+constexpr int TC_SMEM_A = 0;
+constexpr int TC_SMEM_B = 2 * TC_A_BYTES;
+constexpr int TC_SMEM_N = TC_SMEM_B + TC_B_STAGES * TC_B_BYTES;   // 2 x 256 int32 norms
+constexpr int TC_SMEM_BAR = TC_SMEM_N + 2 * TILE_DB * 4;
+constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
+constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
+
+// One database image of a run (shard): all query tiles [atile0, atile0 + ntiles_q) are matched
+// against rows [db_row0, db_row0 + npad).
+struct RunImage {
+    int32_t img;        // database image index i
+    int32_t n;          // real keys in image i (>0)
+    int32_t db_row0;    // first device row of image i
+    int32_t ntiles_db;  // npad_i / 256
+    int32_t atile0;     // first 128-row query tile (device row / 128) = doff[start_i] / 128
+    int32_t start_img;  // first query image j
+    int32_t unit0;      // first work unit of this image inside the run
+    int32_t nunits;     // number of query tiles
+    int64_t pair0;      // index of pair (start_img, i) in the shard's pair list
+};
+
+struct MatchParams {
+    const uint8_t *keys_sw;     // swizzled padded descriptors
+    const int32_t *norms;       // per device row
+    const RunImage *run_imgs;   // K entries, unit0 ascending
+    int32_t num_run_imgs;
+    int32_t unit_begin;         // units [unit_begin, unit_end) are processed by this launch
+    int32_t unit_end;
+    double ratio_sq;            // ratio*ratio evaluated on the host in double (keys2a.cpp:362)
+    // candidate list (tensor-core kernel): SoA int32 [6][cand_cap]: slot, qrow, db0, col0, nvalid, d1u
+    int32_t *cand;
+    int32_t cand_cap;
+    // match list (unordered): slot keys + idx2 values
+    uint32_t *match_slot;
+    int32_t *match_idx2;
+    int32_t match_cap;
+    int32_t *counters;          // [0] = #candidates, [1] = #matches, [2] = overflow flag, [3] = d0 mismatches
+};
+
+// byte offset of 16-byte chunk c (0..7) of device row r in the swizzled layout
+__host__ __device__ __forceinline__ size_t sw_chunk_offset(int64_t row, int c)
+{
+    return (size_t) (row >> 3) * 1024 + (size_t) (row & 7) * 128 + (size_t) ((c ^ (int) (row & 7)) << 4);
+}
+
+// find the run image that owns work unit u (binary search over unit0)
+__device__ __forceinline__ int find_run_image(const RunImage *imgs, int K, int u)
+{
+    int lo = 0, hi = K - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (imgs[mid].unit0 <= u) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+}  // namespace match
+}  // namespace bsfm

@@ -1,0 +1,114 @@
+/* bsfm_b200.h -- C ABI of libbsfm_b200.so, the B200-native (sm_100a) drop-in for the two
+ * data-parallel hot paths of snavely/bundler_sfm.  Plain pointers and sizes only; no torch types.
+ * Every entry point cites the reference interface (file:line under /root/reference) it replaces.
+ *
+ *   MATCH  : all-pairs 128-D uint8 SIFT 2-NN + ratio test  (src/keys2a.cpp, src/KeyMatchFull.cpp)
+ *   BA     : sparse Levenberg-Marquardt bundle adjustment   (lib/sfm-driver/sfm.c, lib/sba-1.5)
+ *
+ * Error convention: functions returning int/int64 return a negative value on failure and store a
+ * message retrievable with bsfm_last_error().  There is NO CPU fallback: without a CUDA device (or
+ * without the sm_100a kernels) every compute entry point fails loudly.
+ */
+#ifndef BSFM_B200_H
+#define BSFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSFM_OK              0
+#define BSFM_ERR_CUDA       -2   /* CUDA runtime / launch error (message has the detail)        */
+#define BSFM_ERR_ARG        -3   /* invalid argument                                            */
+#define BSFM_ERR_CAPACITY   -4   /* caller-provided output buffer too small (needed size known)  */
+#define BSFM_ERR_NO_DEVICE  -5   /* no usable sm_100 GPU                                        */
+#define BSFM_ERR_UNSUPPORTED -6  /* reference feature outside the GPU path  */
+
+/* last error message of the calling thread's most recent failing call ("" if none) */
+const char *bsfm_last_error(void);
+/* library version string, e.g. "bsfm_b200 0.1 (sm_100a)" */
+const char *bsfm_version(void);
+/* number of kernels launched by this process through the library so far (bench `gpu_launches`) */
+int64_t bsfm_kernel_launches(void);
+/* select the CUDA device used by subsequent calls of this thread's process (default: current) */
+int bsfm_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * MATCH
+ * ---------------------------------------------------------------------------------------------- */
+
+/* kernel selector for the matcher (env BSFM_MATCH_KERNEL overrides the default):
+ *   0 = tcgen05 kind::i8 tensor-core kernel (TMA bulk loads, TMEM accumulators)   [default]
+ *   1 = DP4A CUDA-core kernel (cross-check / fallback-free second implementation)            */
+#define BSFM_MATCH_KERNEL_TC    0
+#define BSFM_MATCH_KERNEL_DP4A  1
+
+/* Replaces  std::vector<KeypointMatch> MatchKeys(int num_keys1, unsigned char *k1,
+ *                                               int num_keys2, unsigned char *k2,
+ *                                               double ratio, int max_pts_visit)
+ *           src/keys2a.h:99-102, src/keys2a.cpp:375-424   (and the tree overload :347-372 via the
+ *           C++ shim in shim/keys2a_b200.cpp).
+ * For every query i in k1 finds the two nearest keys in k2 under squared L2 (int32) and emits
+ * (i, nn0) iff (double)d0 < ratio*ratio*(double)d1 (keys2a.cpp:362), ascending in i.
+ * The search is EXACT (== the reference with max_pts_visit = 0; the reference default of 200 is an
+ * approximation).  k1: n1 x 128 bytes, k2: n2 x 128 bytes, host memory.
+ * out_pairs: cap x 2 int32 (idx1, idx2).  Returns the number of matches (>=0); if it exceeds cap,
+ * only the first cap are written and the full count is still returned.                       */
+int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio,
+                    int32_t *out_pairs, int cap);
+
+/* Device-resident key database for the KeyMatchFull all-pairs loop (src/KeyMatchFull.cpp:93-151).
+ * keys  : concatenation of all images' descriptors (sum n_i x 128 bytes), HOST memory
+ * key_off: N+1 prefix offsets in keys (units of descriptors)
+ * Uploads once, computes squared norms and writes the padded, 128B-swizzled tile layout the
+ * tensor-core kernel streams with TMA bulk copies (DESIGN.md "HBM layout").                    */
+typedef struct bsfm_keydb bsfm_keydb;
+bsfm_keydb *bsfm_keydb_create(const uint8_t *keys, const int64_t *key_off, int num_images);
+/* same, but `keys_dev` already lives in device memory (bench `value` leg; torch data_ptr()) */
+bsfm_keydb *bsfm_keydb_create_dev(const uint8_t *keys_dev, const int64_t *key_off, int num_images);
+void bsfm_keydb_destroy(bsfm_keydb *db);
+
+/* Number of ordered image pairs (j < i, j >= i - window_radius if window_radius > 0) the
+ * KeyMatchFull loop visits (KeyMatchFull.cpp:105-121), in its order: i ascending, j ascending.
+ * Pairs with an empty image are included (they produce 0 matches).                           */
+int64_t bsfm_match_num_pairs(int num_images, int window_radius);
+
+/* Runs the pair loop of KeyMatchFull.cpp:105-151 for the database images i in [img_begin, img_end)
+ * (all j < i inside the window), i.e. one contiguous shard of the pair list -- the unit of
+ * multi-GPU sharding.  Results stay on the device inside `db` until fetched.
+ * Returns the total number of matches found in the shard (>=0) or a negative error.          */
+int64_t bsfm_match_run(bsfm_keydb *db, int img_begin, int img_end, int window_radius, double ratio);
+
+/* Copies the result of the last bsfm_match_run to host memory.
+ * pair_counts : one int32 per pair of the shard, KeyMatchFull order
+ * matches     : total x 2 int32 (idx_in_j, idx_in_i), grouped by pair in the same order, ascending
+ *               idx_in_j inside a pair (keys2a.cpp:356-365)
+ * Returns BSFM_OK or BSFM_ERR_CAPACITY.                                                       */
+int bsfm_match_fetch(bsfm_keydb *db, int32_t *pair_counts, int64_t pair_cap,
+                     int32_t *matches, int64_t match_cap);
+/* device pointers of the same two arrays (valid until the next run/destroy) for an NCCL
+ * all-gather straight from HBM; *num_pairs / *num_matches receive the element counts          */
+int bsfm_match_result_dev(bsfm_keydb *db, const int32_t **pair_counts_dev, int64_t *num_pairs,
+                          const int32_t **matches_dev, int64_t *num_matches);
+/* number of pairs in the shard of the last run */
+int64_t bsfm_match_shard_pairs(bsfm_keydb *db);
+/* timing of the last bsfm_match_run measured with CUDA events on the launching stream:
+ * ms[0] = search kernel(s), ms[1] = verify+sort+finalize, ms[2] = whole run; launches = kernels  */
+int bsfm_match_last_timing(bsfm_keydb *db, float ms[3], int *launches);
+
+/* One-call host API: KeyMatchFull's loop over host buffers (upload + run + fetch).
+ * Returns total matches or negative error; BSFM_ERR_CAPACITY if match_cap too small.          */
+int64_t bsfm_match_all_pairs(const uint8_t *keys, const int64_t *key_off, int num_images,
+                             int window_radius, double ratio,
+                             int32_t *pair_counts, int64_t pair_cap,
+                             int32_t *matches, int64_t match_cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * BA  (declared in bsfm_b200_ba.h; kept separate because it mirrors the reference structs)
+ * ---------------------------------------------------------------------------------------------- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSFM_B200_H */

@@ -1,0 +1,43 @@
+/* oracle/ref_sba_wrap.c -- TEST INFRASTRUCTURE ONLY.
+ * Glue for the UNMODIFIED reference BA (lib/sba-1.5 + lib/sfm-driver) built into
+ * oracle/_ref/libref_sba.so:
+ *   - lmdif_/lmdif1_ stubs (minpack; only reached from camera_refine, never from run_sfm,
+ *     lib/sfm-driver/sfm.c:1016-1100)
+ *   - ref_hook_sba_motstr_levmar: sfm.c is compiled with -Dsba_motstr_levmar=<this> so the
+ *     info[10] vector that run_sfm only prints (sfm.c:872-873) can be read back by tests.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sba.h"
+
+void lmdif_(void)  { fprintf(stderr, "lmdif_ stub reached\n");  abort(); }
+void lmdif1_(void) { fprintf(stderr, "lmdif1_ stub reached\n"); abort(); }
+
+static double g_last_info[SBA_INFOSZ];
+static int g_last_ret = -2;
+
+int ref_hook_sba_motstr_levmar(const int n, const int m, const int mcon, char *vmask,
+        double *p, const int cnp, const int pnp, double *x, double *covx, const int mnp,
+        void (*proj)(int j, int i, double *aj, double *bi, double *xij, void *adata),
+        void (*projac)(int j, int i, double *aj, double *bi, double *Aij, double *Bij, void *adata),
+        void *adata, const int itmax, const int verbose, const double opts[SBA_OPTSSZ],
+        double info[SBA_INFOSZ], int use_constraints, camera_constraints_t *constraints,
+        int use_point_constraints, point_constraints_t *point_constraints,
+        double *Vout, double *Sout, double *Uout, double *Wout)
+{
+    int verb = verbose;
+    const char *q = getenv("REF_SBA_VERBOSE");
+    if (q) verb = atoi(q);
+    g_last_ret = sba_motstr_levmar(n, m, mcon, vmask, p, cnp, pnp, x, covx, mnp, proj, projac,
+                                   adata, itmax, verb, opts, info, use_constraints, constraints,
+                                   use_point_constraints, point_constraints, Vout, Sout, Uout, Wout);
+    memcpy(g_last_info, info, sizeof(g_last_info));
+    return g_last_ret;
+}
+
+void ref_last_info(double *info10, int *ret)
+{
+    memcpy(info10, g_last_info, sizeof(g_last_info));
+    if (ret) *ret = g_last_ret;
+}

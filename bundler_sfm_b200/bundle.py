@@ -1,0 +1,149 @@
+"""Host-side mirror of the reference BA interface on top of the C ABI.
+
+Reference (file:line under /root/reference):
+  run_sfm(num_pts, num_cameras, ncons, vmask, projections, est_focal_length, const_focal_length,
+          undistort, explicit_camera_centers, init_camera_params, init_pts, use_constraints,
+          use_point_constraints, points_constraints, point_constraint_weight, fix_points,
+          optimize_for_fisheye, eps2, Vout, Sout, Uout, Wout)          lib/sfm-driver/sfm.h:68-86
+  camera_params_t                                                       lib/sfm-driver/sfm.h:32-51
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import load_library, check
+
+NUM_CAMERA_PARAMS = 9
+
+
+class CameraParams(ctypes.Structure):
+    """== camera_params_t (lib/sfm-driver/sfm.h:32-51) / bsfm_camera_params_t"""
+    _fields_ = [
+        ("R", ctypes.c_double * 9), ("t", ctypes.c_double * 3), ("f", ctypes.c_double), ("k", ctypes.c_double * 2),
+        ("k_inv", ctypes.c_double * 6), ("constrained", ctypes.c_char * NUM_CAMERA_PARAMS),
+        ("constraints", ctypes.c_double * NUM_CAMERA_PARAMS), ("weights", ctypes.c_double * NUM_CAMERA_PARAMS),
+        ("K_known", ctypes.c_double * 9), ("k_known", ctypes.c_double * 5), ("fisheye", ctypes.c_char),
+        ("known_intrinsics", ctypes.c_char), ("f_cx", ctypes.c_double), ("f_cy", ctypes.c_double),
+        ("f_rad", ctypes.c_double), ("f_angle", ctypes.c_double), ("f_focal", ctypes.c_double),
+        ("f_scale", ctypes.c_double), ("k_scale", ctypes.c_double),
+    ]
+
+
+def make_cameras(R, c, f, k, constrained=None, constraints=None, weights=None):
+    m = len(f)
+    cams = (CameraParams * m)()
+    for j in range(m):
+        cams[j].R[:] = list(np.asarray(R[j], float).reshape(9))
+        cams[j].t[:] = list(np.asarray(c[j], float))
+        cams[j].f = float(f[j])
+        cams[j].k[:] = list(np.asarray(k[j], float))
+        cams[j].f_scale = 1.0
+        cams[j].k_scale = 1.0
+        if constrained is not None:
+            ctypes.memmove(ctypes.addressof(cams[j]) + CameraParams.constrained.offset,
+                           bytes(bytearray(int(v) for v in constrained[j])), NUM_CAMERA_PARAMS)
+            cams[j].constraints[:] = list(np.asarray(constraints[j], float))
+            cams[j].weights[:] = list(np.asarray(weights[j], float))
+    return cams
+
+
+def cameras_to_arrays(cams):
+    m = len(cams)
+    R = np.array([list(cams[j].R) for j in range(m)])
+    c = np.array([list(cams[j].t) for j in range(m)])
+    f = np.array([cams[j].f for j in range(m)])
+    k = np.array([list(cams[j].k) for j in range(m)])
+    return R, c, f, k
+
+
+def _bind_run_sfm(fn):
+    c = ctypes
+    fn.argtypes = [c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int,
+                   c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_double, c.c_int, c.c_int, c.c_double,
+                   c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    return fn
+
+
+def call_run_sfm(fn, scene, est_focal_length=1, undistort=1, explicit_camera_centers=1, ncons=0, eps2=1e-12,
+                 use_constraints=0, constrained=None, constraints=None, weights=None,
+                 use_point_constraints=0, points_constraints=None, point_constraint_weight=0.0,
+                 extra_info=False):
+    """Calls a run_sfm-shaped C function (ours or the reference's) on a scene dict (synth.ba_scene).
+    Returns a dict with the refined R, c, f, k, pts (+ info when the callee provides it)."""
+    vmask = np.ascontiguousarray(scene["vmask"], dtype=np.int8)
+    n, m = vmask.shape
+    proj = np.ascontiguousarray(scene["projections"], dtype=np.float64)
+    cams = make_cameras(scene["R"], scene["c"], scene["f"], scene["k"], constrained, constraints, weights)
+    pts = np.ascontiguousarray(scene["pts"], dtype=np.float64).copy()
+    pc = None
+    if use_point_constraints:
+        pc = np.ascontiguousarray(points_constraints, dtype=np.float64)
+    args = [n, m, ncons, vmask.ctypes.data, proj.ctypes.data, est_focal_length, 0, undistort, explicit_camera_centers,
+            ctypes.addressof(cams), pts.ctypes.data, use_constraints, use_point_constraints,
+            pc.ctypes.data if pc is not None else None, float(point_constraint_weight), 0, 0, float(eps2),
+            None, None, None, None]
+    info = np.zeros(10)
+    if extra_info:
+        rc = fn(*args, info.ctypes.data)
+    else:
+        rc = fn(*args)
+    R, c, f, k = cameras_to_arrays(cams)
+    return {"rc": rc, "R": R, "c": c, "f": f, "k": k, "pts": pts, "info": info}
+
+
+_run_sfm = None
+
+
+def run_sfm(scene, **kw):
+    """GPU run_sfm (bsfm_run_sfm).  Raises on BSFM errors; returns the refined scene + info[10]."""
+    global _run_sfm
+    lib = load_library()
+    if _run_sfm is None:
+        fn = lib.bsfm_run_sfm
+        _bind_run_sfm(fn)
+        fn.argtypes = fn.argtypes + [ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+        _run_sfm = fn
+    out = call_run_sfm(_run_sfm, scene, extra_info=True, **kw)
+    check(out["rc"], "bsfm_run_sfm")
+    return out
+
+
+def last_timing():
+    lib = load_library()
+    ms = (ctypes.c_float * 6)()
+    it, ln = ctypes.c_int(), ctypes.c_int()
+    lib.bsfm_ba_last_timing(ms, ctypes.byref(it), ctypes.byref(ln))
+    names = ["setup_ms", "jacobian_uvw_ms", "schur_ms", "cholesky_ms", "backsub_eval_ms", "total_ms"]
+    d = {k: float(v) for k, v in zip(names, ms)}
+    d["iterations"] = it.value
+    d["launches"] = ln.value
+    return d
+
+
+def reprojection_rmse(scene, sol):
+    """sqrt(mean squared reprojection error) of a solution under the Bundler camera model
+    (lib/sfm-driver/sfm.c:302-380), computed in numpy -- a test/bench metric, not a product path."""
+    vmask = scene["vmask"]
+    pi, cj = np.nonzero(vmask)
+    R = sol["R"].reshape(-1, 3, 3)
+    Pc = np.einsum("oij,oj->oi", R[cj], sol["pts"][pi] - sol["c"][cj])
+    f = sol["f"][cj]
+    p = -Pc[:, :2] * f[:, None] / Pc[:, 2:3]
+    rsq = (p ** 2).sum(1) / (f * f)
+    k = sol["k"][cj]
+    p = p * (1.0 + k[:, 0] * rsq + k[:, 1] * rsq * rsq)[:, None]
+    e = scene["projections"] - p
+    return float(np.sqrt((e ** 2).sum() / e.shape[0]))
+
+
+def smoke(loader):
+    """small BA solve on cuda:0 checked against the oracle (reference build when present)"""
+    from . import synth
+    scene = synth.ba_scene(10, 500, 4, seed=3)
+    got = run_sfm(scene)
+    ref = loader.run_sfm_oracle(scene)
+    r_gpu, r_ref = np.sqrt(got["info"][1] / scene["projections"].shape[0]), np.sqrt(ref["info"][1] / scene["projections"].shape[0])
+    assert abs(r_gpu - r_ref) <= 1e-5, (r_gpu, r_ref)
+    assert int(got["info"][5]) == int(ref["info"][5]) and int(got["info"][6]) == int(ref["info"][6])
+    print(f"[smoke] BA ok: {int(got['info'][5])} LM iterations, RMSE {r_gpu:.6f} (oracle {r_ref:.6f})")

@@ -36,3 +36,46 @@ def random_descriptors(n, seed, lo=0, hi=256):
     """uniform uint8 descriptors (adversarial/edge-case tests)"""
     rng = np.random.default_rng(seed)
     return rng.integers(lo, hi, size=(n, 128), dtype=np.int64).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+# BA scenes (SURVEY.md 8d): cameras on a ring of radius 6 looking at the origin (Bundler convention:
+# the camera looks down -z, P = R (X - c)), f = 800, k = 0; points uniform in [-1,1]^3; each point is
+# seen by L cameras; pixel noise N(0, 0.5^2); perturbed initial estimate.
+# ------------------------------------------------------------------------------------------------
+def ba_scene(num_cameras=50, num_points=20000, views_per_point=5, seed=1234, pixel_noise=0.5,
+             pt_noise=0.02, cam_noise=0.01, f_noise=0.01, focal=800.0):
+    """Returns a dict with the arguments of run_sfm (numpy arrays):
+    vmask [n,m] int8, projections [nvis,2], R [m,9], c [m,3] (camera centres), f [m], k [m,2], pts [n,3]
+    (the perturbed initial estimate) and the ground truth (gt_*)."""
+    rng = np.random.default_rng(seed)
+    m, n, L = num_cameras, num_points, views_per_point
+    ang = 2.0 * np.pi * np.arange(m) / m
+    c = np.stack([6.0 * np.cos(ang), 0.3 * np.sin(3 * ang), 6.0 * np.sin(ang)], 1)
+    R = np.zeros((m, 3, 3))
+    for j in range(m):
+        z = c[j] / np.linalg.norm(c[j])          # camera looks down -z => z axis points away from the scene
+        up = np.array([0.0, 1.0, 0.0])
+        xax = np.cross(up, z); xax /= np.linalg.norm(xax)
+        yax = np.cross(z, xax)
+        R[j] = np.stack([xax, yax, z], 0)
+    pts = rng.uniform(-1.0, 1.0, size=(n, 3))
+    vmask = np.zeros((n, m), np.int8)
+    step = max(m // L, 1)
+    starts = (np.arange(n) * 7) % m
+    for k in range(L):
+        vmask[np.arange(n), (starts + k * step) % m] = 1
+    pi, cj = np.nonzero(vmask)                    # row-major: point-major, ascending camera
+    Pc = np.einsum("oij,oj->oi", R[cj], pts[pi] - c[cj])
+    proj = -Pc[:, :2] * focal / Pc[:, 2:3]
+    proj = proj + pixel_noise * rng.standard_normal(proj.shape)
+    scene = {
+        "vmask": vmask, "projections": np.ascontiguousarray(proj),
+        "gt_pts": pts, "gt_c": c, "gt_R": R.reshape(m, 9).copy(), "gt_f": np.full(m, focal),
+        "R": R.reshape(m, 9).copy(),
+        "c": c + cam_noise * rng.standard_normal(c.shape),
+        "f": focal * (1.0 + f_noise * rng.standard_normal(m)),
+        "k": np.zeros((m, 2)),
+        "pts": pts + pt_noise * rng.standard_normal(pts.shape),
+    }
+    return scene

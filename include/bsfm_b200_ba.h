@@ -1,0 +1,110 @@
+/* bsfm_b200_ba.h -- C ABI of the BA hot path of libbsfm_b200.so (sparse Levenberg-Marquardt bundle
+ * adjustment on one B200).  Replaces, behind the reference's own call boundary:
+ *
+ *   run_sfm(...)                 lib/sfm-driver/sfm.h:68-86,  lib/sfm-driver/sfm.c:592-1003
+ *   sba_motstr_levmar_x(...)     lib/sba-1.5/sba.h:127-138,   lib/sba-1.5/sba_levmar.c:457-2081
+ *
+ * The structs below restate the reference's interface types field-for-field so that a caller
+ * compiled against the reference headers can pass its own objects unchanged (same size, same
+ * offsets; checked by tests/test_abi.py against the compiled reference when it is available).
+ * There is no CPU fallback; unsupported reference options return BSFM_ERR_UNSUPPORTED.
+ */
+#ifndef BSFM_B200_BA_H
+#define BSFM_B200_BA_H
+
+#include <stdint.h>
+#include "bsfm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSFM_NUM_CAMERA_PARAMS 9     /* lib/sfm-driver/sfm.h:29 */
+#define BSFM_POLY_INVERSE_DEGREE 6   /* lib/sfm-driver/sfm.h:30 */
+
+/* == camera_params_t, lib/sfm-driver/sfm.h:32-51 */
+typedef struct {
+    double R[9];
+    double t[3];
+    double f;
+    double k[2];
+    double k_inv[BSFM_POLY_INVERSE_DEGREE];
+    char constrained[BSFM_NUM_CAMERA_PARAMS];
+    double constraints[BSFM_NUM_CAMERA_PARAMS];
+    double weights[BSFM_NUM_CAMERA_PARAMS];
+    double K_known[9];
+    double k_known[5];
+    char fisheye;
+    char known_intrinsics;
+    double f_cx, f_cy;
+    double f_rad, f_angle;
+    double f_focal;
+    double f_scale, k_scale;
+} bsfm_camera_params_t;
+
+/* == v3_t, lib/matrix/vector.h:65-67 */
+typedef struct { double p[3]; } bsfm_v3_t;
+
+/* == camera_constraints_t / point_constraints_t, lib/sba-1.5/sba.h:80-90 */
+typedef struct { char *constrained; double *constraints; double *weights; } bsfm_camera_constraints_t;
+typedef struct { char constrained; double constraints[3]; double weight; } bsfm_point_constraints_t;
+
+/* Jacobian mode of the solver (env BSFM_BA_JAC overrides: "fd" | "analytic")
+ *   0 = forward finite differences with the reference's step rule d = max(1e-4*|p|, 1e-6)
+ *       (lib/sba-1.5/sba_levmar_wrap.c:203-256, sba.h:52-53) -- what run_sfm uses (projac = NULL,
+ *       lib/sfm-driver/sfm.c:820-828); the parity mode and the default.
+ *   1 = analytic 2x9 / 2x3 Jacobians of the same camera model (include/snavely_reprojection_error.h:58-92
+ *       restated in the SBA parameterisation)                            */
+#define BSFM_BA_JAC_FD        0
+#define BSFM_BA_JAC_ANALYTIC  1
+
+/* Camera model descriptor: what sfm_project_point3 (lib/sfm-driver/sfm.c:503-552) reads from its
+ * `adata` (sfm_global_t) -- made explicit because a GPU solver cannot call an opaque callback.   */
+typedef struct {
+    int est_focal_length;         /* aj[6] = f * f_scale is a parameter (else f_fixed[j] is used)   */
+    int undistort;                /* two radial terms k1,k2 (scaled by k_scale) are parameters       */
+    int explicit_camera_centers;  /* aj[0..2] is the camera centre c (P = R (X - c)), else P = R X + t */
+    double f_scale, k_scale;      /* 0.001 and 5.0 in run_sfm (sfm.c:634-635)                        */
+    const double *R_init;         /* m x 9 row-major initial rotations (init_params[j].R)            */
+    const double *f_fixed;        /* m focal lengths used when est_focal_length == 0                 */
+} bsfm_sfm_model_t;
+
+/* Core solver == sba_motstr_levmar_x (lib/sba-1.5/sba_levmar.c:457-2081) with func/fjac/adata
+ * replaced by the explicit camera model.  Arguments keep the reference's meaning:
+ *   n points, m cameras, mcon leading cameras held fixed, vmask n x m, p = (a_1..a_m, b_1..b_n)
+ *   in/out, cnp in {6,7,8,9}, pnp = 3, x = measurements (2 per visible projection, point-major),
+ *   covx must be NULL, mnp = 2, itmax, verbose, opts[6] (reads opts[5], sba_levmar.c:610),
+ *   info[10] (sba_levmar.c:2028-2049), camera / point constraints as in sba.h:80-90.
+ * Vout/Sout/Uout/Wout must be NULL (BSFM_ERR_UNSUPPORTED otherwise).
+ * Returns the number of iterations (>=0) like the reference, SBA_ERROR (-1) where the reference
+ * returns it, or another negative BSFM_ERR_* code.                                              */
+int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,
+                                 const double *x, const double *covx, int mnp,
+                                 const bsfm_sfm_model_t *model, int jac_mode,
+                                 int itmax, int verbose, const double opts[6], double info[10],
+                                 int use_constraints, const bsfm_camera_constraints_t *constraints,
+                                 int use_point_constraints, const bsfm_point_constraints_t *point_constraints,
+                                 double *Vout, double *Sout, double *Uout, double *Wout);
+
+/* == run_sfm (lib/sfm-driver/sfm.h:68-86): same arguments, same in/out semantics
+ * (init_camera_params and init_pts are overwritten with the solution, sfm.c:876-929; prints
+ * "[run_sfm] Number of iterations" / "info[6]" like sfm.c:872-873), plus `info_out` (nullable,
+ * 10 doubles) and an int return (0 or negative error) which the void reference lacks.
+ * GPU path covers fix_points == 0, optimize_for_fisheye == 0, const_focal_length == 0 and cameras
+ * with known_intrinsics == 0; anything else returns BSFM_ERR_UNSUPPORTED.                       */
+int bsfm_run_sfm(int num_pts, int num_cameras, int ncons, char *vmask, double *projections,
+                 int est_focal_length, int const_focal_length, int undistort, int explicit_camera_centers,
+                 bsfm_camera_params_t *init_camera_params, bsfm_v3_t *init_pts,
+                 int use_constraints, int use_point_constraints, bsfm_v3_t *points_constraints,
+                 double point_constraint_weight, int fix_points, int optimize_for_fisheye, double eps2,
+                 double *Vout, double *Sout, double *Uout, double *Wout, double *info_out);
+
+/* Per-phase device time (ms, CUDA events) of the last solve of this thread:
+ * [0] setup (H2D, CSR, Schur structure)  [1] residual/Jacobian/U/V/W  [2] Schur S assembly
+ * [3] dense Cholesky + solves  [4] back-substitution/update/function eval  [5] whole solve      */
+int bsfm_ba_last_timing(float ms[6], int *iterations, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSFM_B200_BA_H */

@@ -77,6 +77,13 @@ def ref_sba():
     global _ref_sba
     if _ref_sba is None:
         os.environ.setdefault("OPENBLAS_CORETYPE", "HASWELL")
+        if not os.path.exists(os.path.join(_HERE, "_ref", "libref_sba.so")):
+            return None
+        # OpenBLAS 0.3.15 from the venv's opencv wheel needs its sibling libquadmath/libgfortran
+        for dep in ("libquadmath-2284e583.so.0.0.0", "libgfortran-83c28eba.so.5.0.0", "libopenblasp-r0-59ffcd50.3.15.so"):
+            dp = os.path.join(_OB, dep)
+            if os.path.exists(dp):
+                ctypes.CDLL(dp, mode=ctypes.RTLD_GLOBAL)
         lib = _load(os.path.join(_HERE, "_ref", "libref_sba.so"))
         if lib is None:
             return None
@@ -125,3 +132,54 @@ def match_all_pairs_port(keys_list, window_radius=-1, ratio=0.6, min_matches=16)
     buf = ctypes.create_string_buffer(max(need, 1))
     port().oracle_match_all_pairs(keys.ctypes.data, key_off.ctypes.data, N, window_radius, float(ratio), min_matches, buf, need, None)
     return buf.raw[:need].decode(), counts
+
+
+# ---- BA helpers -----------------------------------------------------------------------------
+def run_sfm_ref(scene, quiet=True, **kw):
+    """run the UNMODIFIED reference run_sfm (oracle/_ref/libref_sba.so) on a scene dict"""
+    from bundler_sfm_b200 import bundle
+    lib = ref_sba()
+    assert lib is not None, "oracle/_ref/libref_sba.so not built"
+    fn = lib.run_sfm
+    bundle._bind_run_sfm(fn)
+    fn.restype = None
+    if quiet:
+        os.environ["REF_SBA_VERBOSE"] = "0"
+    saved = None
+    if quiet:
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        os.close(devnull)
+    try:
+        out = bundle.call_run_sfm(fn, scene, **kw)
+    finally:
+        if saved is not None:
+            os.dup2(saved, 1)
+            os.close(saved)
+    info = np.zeros(10)
+    ret = ctypes.c_int()
+    lib.ref_last_info.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.ref_last_info(info.ctypes.data, ctypes.byref(ret))
+    out["info"] = info
+    out["rc"] = ret.value
+    return out
+
+
+def run_sfm_oracle(scene, **kw):
+    """reference build when present, else the C restatement (oracle/ba_oracle.c)"""
+    if ref_sba() is not None:
+        return run_sfm_ref(scene, **kw)
+    return run_sfm_port(scene, **kw)
+
+
+def run_sfm_port(scene, quiet=True, **kw):
+    """C restatement oracle/ba_oracle.c (oracle_run_sfm has run_sfm's signature + info[10])"""
+    from bundler_sfm_b200 import bundle
+    fn = port().oracle_run_sfm
+    bundle._bind_run_sfm(fn)
+    fn.argtypes = fn.argtypes + [ctypes.c_void_p]
+    fn.restype = ctypes.c_int
+    return bundle.call_run_sfm(fn, scene, extra_info=True, **kw)

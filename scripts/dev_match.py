@@ -13,7 +13,8 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 imgs = synth.sift_like_descriptors(N, K, seed=7)
 keys, key_off = keymatch.concat_keys(imgs)
 res = {}
-for name, sel in (("tc", "0"), ("dp4a", "1")):
+which = sys.argv[3] if len(sys.argv) > 3 else "both"
+for name, sel in [x for x in (("tc", "0"), ("dp4a", "1")) if which in ("both", x[0])]:
     os.environ["BSFM_MATCH_KERNEL"] = sel
     db = keymatch.KeyDatabase(keys, key_off)
     for rep in range(3):
@@ -29,4 +30,5 @@ for name, sel in (("tc", "0"), ("dp4a", "1")):
           f"wall_ms={wall*1e3:.2f} launches={tm['launches']} desc-pairs/s={dp/(tm['total_ms']*1e-3):.3e} "
           f"TOPS(search)={dp*256/(tm['search_ms']*1e-3)/1e12:.1f}", flush=True)
     db.close()
-print("tc == dp4a:", np.array_equal(res["tc"][0], res["dp4a"][0]) and np.array_equal(res["tc"][1], res["dp4a"][1]))
+if which == "both":
+    print("tc == dp4a:", np.array_equal(res["tc"][0], res["dp4a"][0]) and np.array_equal(res["tc"][1], res["dp4a"][1]))

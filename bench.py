@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of bundler_sfm_b200 (contract: see the task prompt / DESIGN.md section 6).
+
+Default workload (BASELINE.json configs[1]): synthetic BA, 50 cameras / 20,000 points / 100,000
+observations; one "step" = one full run_sfm-equivalent LM solve.  Metric: LM iterations / second.
+  value : solver called with vmask / measurements / parameters already resident in HBM
+  e2e   : bsfm_run_sfm (the reference-facing C-ABI call) with HOST buffers, H2D/D2H inside the timing
+The same JSON line carries a "match" object: KeyMatchFull config 4 (500 images x 5000 keys, all
+pairs) sharded over the N ranks with an NCCL all-gather of the match table (descriptor-pairs/s).
+`--workload match` makes that the headline line instead.  `--impl reference` times the unmodified
+reference CPU code (oracle/_ref, built from /root/reference) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BA_CFG = dict(num_cameras=50, num_points=20000, views_per_point=5)
+MATCH_CFG = dict(num_images=500, keys_per_image=5000)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (recipe in B200_PROFILING.md)"""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def _ref_ba_worker(args):
+    seed, nsolves = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from bundler_sfm_b200 import synth
+    from oracle import loader
+    scene = synth.ba_scene(seed=seed, **BA_CFG)
+    its = 0
+    t0 = time.perf_counter()
+    for _ in range(nsolves):
+        out = loader.run_sfm_oracle(scene)
+        its += int(out["info"][5])
+    return its, time.perf_counter() - t0
+
+
+def run_reference_ba(steps, warmup, procs):
+    """`procs` independent reference processes (the reference is single-threaded and not re-entrant,
+    SURVEY.md F6), each solving the config-2 scene `steps` times: aggregate LM iterations / s."""
+    import multiprocessing as mp
+    from oracle import loader
+    kind = "reference" if loader.ref_sba() is not None else "port"
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        if warmup > 0:
+            pool.map(_ref_ba_worker, [(1234 + r, 1) for r in range(procs)])
+        t0 = time.perf_counter()
+        res = pool.map(_ref_ba_worker, [(1234 + r, steps) for r in range(procs)])
+        wall = time.perf_counter() - t0
+    its = sum(r[0] for r in res)
+    return its / wall, wall, kind, its
+
+
+def _ref_match_worker(args):
+    seed, npairs = args
+    from bundler_sfm_b200 import synth
+    from oracle import loader
+    imgs = synth.sift_like_descriptors(2, MATCH_CFG["keys_per_image"], seed=seed)
+    lib = loader.ref_match()
+    t0 = time.perf_counter()
+    for _ in range(npairs):
+        if lib is not None:
+            loader.match_pair_ref(imgs[0], imgs[1], 0.6, 200)     # stock KeyMatchFull: ANN priority search, 200-visit cap
+        else:
+            loader.match_pair_port(imgs[0], imgs[1], 0.6)
+    return npairs, time.perf_counter() - t0
+
+
+def run_reference_match(pairs_per_proc, procs):
+    import multiprocessing as mp
+    from oracle import loader
+    kind = "reference" if loader.ref_match() is not None else "port"
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_ref_match_worker, [(7 + r, 1) for r in range(procs)])
+        t0 = time.perf_counter()
+        res = pool.map(_ref_match_worker, [(7 + r, pairs_per_proc) for r in range(procs)])
+        wall = time.perf_counter() - t0
+    npairs = sum(r[0] for r in res)
+    K = MATCH_CFG["keys_per_image"]
+    return npairs * K * K / wall, npairs / wall, wall, kind, npairs
+
+
+def main_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    if args.workload == "match":
+        pairs_per_proc = max(1, min(args.steps, 40))
+        dps, ips, wall, kind, npairs = run_reference_match(pairs_per_proc, procs)
+        line = {"impl": "reference", "metric": "descriptor-pairs/s (all-pairs SIFT match, KeyMatchFull)", "value": dps, "unit": "descriptor-pairs/s",
+                "n_gpus": args.gpus, "steps": pairs_per_proc, "warmup": 1, "ms_per_step": 1e3 * wall / pairs_per_proc, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "KeyMatchFull config 4: 500 images x 5000 SIFT keys (bounded sample of image pairs)", **MATCH_CFG},
+                "cpu_baseline": {"value": dps, "unit": "descriptor-pairs/s", "cores": procs, "kind": kind,
+                                 "sample": f"{npairs} image pairs of 5000x5000 keys, stock ANN kd-tree priority search (200-visit cap), one process per core"},
+                "e2e": {"value": dps, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "image_pairs_per_s": ips}
+    else:
+        steps = max(1, min(args.steps, 6))
+        ips, wall, kind, its = run_reference_ba(steps, min(args.warmup, 1), procs)
+        line = {"impl": "reference", "metric": "LM iterations/s (sparse bundle adjustment solve)", "value": ips, "unit": "LM iterations/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic BA: 50 cams, 20k points, 100k obs (BASELINE.json configs[1])", **BA_CFG},
+                "cpu_baseline": {"value": ips, "unit": "LM iterations/s", "cores": procs, "kind": kind,
+                                 "sample": f"{steps} full run_sfm solves per process, {procs} independent single-threaded processes (one per host core)"},
+                "e2e": {"value": ips, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def flush_l2(torch, buf):
+    buf.add_(1)   # 512 MB read+write > 126 MB L2
+
+
+def bench_ba(args, torch, dist, rank, world, dev):
+    from bundler_sfm_b200 import bundle, synth
+    os.environ.setdefault("BSFM_BA_VERBOSE", "0")
+    scene = synth.ba_scene(seed=1234 + rank, **BA_CFG)
+    n, m = scene["vmask"].shape
+    nvis = scene["projections"].shape[0]
+    p0, cnp = bundle.pack_params(scene)
+    d_vmask = torch.from_numpy(np.ascontiguousarray(scene["vmask"], np.int8)).to(dev)
+    d_x = torch.from_numpy(np.ascontiguousarray(scene["projections"])).to(dev)
+    d_p0 = torch.from_numpy(p0).to(dev)
+    d_p = d_p0.clone()
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    R_init, f_fixed = scene["R"], scene["f"]
+    devnull = os.open(os.devnull, os.O_WRONLY)
+
+    def solve_resident():
+        d_p.copy_(d_p0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        its, info = bundle.levmar_model(n, m, d_vmask.data_ptr(), d_p.data_ptr(), d_x.data_ptr(), cnp, R_init, f_fixed)
+        return its, time.perf_counter() - t0, bundle.last_timing()
+
+    def solve_e2e():
+        t0 = time.perf_counter()
+        out = bundle.run_sfm(scene)
+        return int(out["info"][5]), time.perf_counter() - t0, out
+
+    # silence the reference-compatible stdout chatter of the solver ("max_pct_change: ...")
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        for _ in range(args.warmup):
+            solve_resident(); solve_e2e()
+        lib = bundle.load_library()
+        launches0 = lib.bsfm_kernel_launches()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
+        its_sum, dev_ms, wall = 0, 0.0, 0.0
+        phase = np.zeros(6)
+        for _ in range(args.steps):
+            flush_l2(torch, flush)
+            its, w, tm = solve_resident()
+            its_sum += its; wall += w; dev_ms += tm["total_ms"]
+        torch.cuda.synchronize()
+        launches = lib.bsfm_kernel_launches() - launches0
+        if dist is not None:
+            dist.barrier()
+        e_its, e_wall = 0, 0.0
+        for _ in range(args.steps):
+            flush_l2(torch, flush)
+            its, w, out = solve_e2e()
+            e_its += its; e_wall += w
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        os.environ["BSFM_BA_TIMING"] = "1"
+        _, _, tm = solve_resident()
+        os.environ.pop("BSFM_BA_TIMING")
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    rmse = float(np.sqrt(out["info"][1] / nvis))
+    # max over ranks (device-event time of the solves), sum of iterations
+    t = torch.tensor([dev_ms * 1e-3, e_wall, float(its_sum), float(e_its)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_s, e_s, its_all, e_its_all = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
+    else:
+        dev_s, e_s, its_all, e_its_all = t[0].item(), t[1].item(), t[2].item(), t[3].item()
+    h2d = n * m + nvis * 16 + m * ctypes.sizeof(bundle.CameraParams) + n * 24
+    d2h = (m * cnp + 3 * n) * 8
+    # algorithmic HBM bytes per LM iteration (SURVEY.md 8d / DESIGN.md): ~0.7 KB per observation + 16 (9m)^2
+    alg_bytes = 0.7e3 * nvis + 16.0 * (9 * m) ** 2
+    iters_one = tm["iterations"]
+    return {
+        "value": its_all / dev_s, "ms_per_step": 1e3 * dev_s / args.steps, "e2e_value": e_its_all / e_s,
+        "h2d": h2d, "d2h": d2h, "launches": int(launches), "clocks": clocks, "rmse": rmse, "iterations_per_solve": iters_one,
+        "phase_ms": {k: v for k, v in tm.items()},
+        "roofline_achieved_gbs": alg_bytes * iters_one / (tm["total_ms"] * 1e-3) / 1e9,
+    }
+
+
+def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image, steps, warmup):
+    from bundler_sfm_b200 import keymatch, synth
+    imgs = synth.sift_like_descriptors(num_images, keys_per_image, seed=7)
+    keys, key_off = keymatch.concat_keys(imgs)
+    sizes = [keys_per_image] * num_images
+    b, e = keymatch.shard_images(sizes, -1, world)[rank]
+    d_keys = torch.from_numpy(keys).to(dev)
+    db = keymatch.KeyDatabase(None, key_off, device_ptr=d_keys.data_ptr())
+
+    def gather():
+        if dist is None:
+            return db.result_dev()[3]
+        # the rank's table stays in HBM: device-to-device copy into torch tensors -> NCCL all-gather over NVLink
+        counts, matches = db.result_to_torch(dev)
+        gc, gm = keymatch.gather_match_table(counts, matches)
+        return gm.shape[0]
+
+    for _ in range(warmup):
+        db.run(b, e, -1, 0.6); gather()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    search_ms, total_matches = 0.0, 0
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        db.run(b, e, -1, 0.6)
+        total_matches = gather()
+        search_ms += db.timing()["search_ms"]
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    # e2e: host descriptors -> upload -> run -> gather -> table on the host
+    t0 = time.perf_counter()
+    db2 = keymatch.KeyDatabase(keys, key_off)
+    db2.run(b, e, -1, 0.6)
+    c_host, m_host = db2.fetch()
+    if dist is not None:
+        keymatch.gather_match_table(c_host, m_host, device=dev)
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    db2.close()
+    t = torch.tensor([wall, search_ms * 1e-3, e2e_wall], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, search_s, e2e_wall = t[0].item(), t[1].item(), t[2].item()
+    npairs = num_images * (num_images - 1) // 2
+    dp = float(npairs) * keys_per_image * keys_per_image
+    db.close()
+    return {"desc_pairs_per_s": dp * steps / wall, "image_pairs_per_s": npairs * steps / wall, "ms_per_pass": 1e3 * wall / steps,
+            "search_kernel_ms_per_pass_max_rank": 1e3 * search_s / steps, "int8_tops_search_kernel": dp * 256 / world / (search_s / steps) / 1e12,
+            "e2e_desc_pairs_per_s": dp / e2e_wall, "matches": int(total_matches), "h2d_bytes": int(keys.nbytes), "images": num_images, "keys_per_image": keys_per_image,
+            "pairs": npairs, "shard": [int(b), int(e)]}
+
+
+def cpu_baseline_ba():
+    from bundler_sfm_b200 import synth
+    from oracle import loader
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    scene = synth.ba_scene(seed=1234, **BA_CFG)
+    t0 = time.perf_counter()
+    out = loader.run_sfm_oracle(scene)
+    dt = time.perf_counter() - t0
+    kind = "reference" if loader.ref_sba() is not None else "port"
+    return {"value": out["info"][5] / dt, "unit": "LM iterations/s", "cores": 1, "kind": kind,
+            "sample": f"one full run_sfm solve of the config ({int(out['info'][5])} LM iterations, {dt:.1f} s), single thread"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ba", choices=["ba", "match"])
+    ap.add_argument("--match-images", type=int, default=MATCH_CFG["num_images"])
+    ap.add_argument("--no-match", action="store_true", help="skip the MATCH sub-benchmark")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    rank, world, local = dist_env()
+    dist = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    warm = max(args.warmup, 3)
+    args.warmup = warm
+    peaks = load_peaks()
+
+    ba = bench_ba(args, torch, dist, rank, world, dev)
+    match = None
+    if not args.no_match:
+        match = bench_match(args, torch, dist, rank, world, dev, args.match_images, MATCH_CFG["keys_per_image"],
+                            steps=max(1, min(args.steps, 3)), warmup=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_ba()
+
+    if rank == 0:
+        i8_peak = 2.0 * peaks["bf16_tflops"]
+        if args.workload == "ba":
+            line = {
+                "metric": "LM iterations/s (sparse bundle adjustment solve)", "value": ba["value"], "unit": "LM iterations/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ba["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic BA: 50 cams, 20k points, 100k obs (BASELINE.json configs[1]); one step = one full LM solve; "
+                                       "N>1 = N independent replicas (BA does not shard); L2 flushed between timed steps (256 MB buffer)",
+                           **BA_CFG, "jacobian": "finite-difference (reference-compatible)", "lm_iterations_per_solve": ba["iterations_per_solve"],
+                           "final_rmse_px": ba["rmse"]},
+                "e2e": {"value": ba["e2e_value"], "unit": "LM iterations/s", "h2d_bytes_per_step": ba["h2d"], "d2h_bytes_per_step": ba["d2h"]},
+                "gpu_launches": ba["launches"], "clocks": ba["clocks"],
+                "roofline": {"bound": "hbm", "achieved": ba["roofline_achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": ba["roofline_achieved_gbs"] / peaks["hbm_gbs"], "traffic": None,
+                             "note": "whole LM iteration: algorithmic bytes 0.7 KB/obs + 16(9m)^2 per iteration / device time; latency-bound at this size; peak " + peaks["source"]},
+                "ba_phase_ms_one_solve": ba["phase_ms"],
+            }
+        else:
+            line = {
+                "metric": "descriptor-pairs/s (all-pairs SIFT match, KeyMatchFull)", "value": match["desc_pairs_per_s"], "unit": "descriptor-pairs/s",
+                "n_gpus": world, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": match["ms_per_pass"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "KeyMatchFull config 4: all pairs of 500 images x 5000 SIFT keys, exact 2-NN + ratio 0.6; descriptors (320 MB) exceed L2",
+                           **MATCH_CFG},
+                "e2e": {"value": match["e2e_desc_pairs_per_s"], "unit": "descriptor-pairs/s", "h2d_bytes_per_step": match["h2d_bytes"], "d2h_bytes_per_step": match["matches"] * 8},
+                "gpu_launches": ba["launches"], "clocks": ba["clocks"],
+                "roofline": {"bound": "tensor", "achieved": match["int8_tops_search_kernel"], "peak": i8_peak, "unit": "TOP/s (int8)",
+                             "frac": match["int8_tops_search_kernel"] / i8_peak, "traffic": None,
+                             "note": "tcgen05 kind::i8 search kernel; 256 int8 ops per descriptor pair; peak = 2 x bf16 dense, " + peaks["source"]},
+            }
+        if match is not None:
+            match["roofline"] = {"bound": "tensor", "achieved": match["int8_tops_search_kernel"], "peak": i8_peak, "unit": "TOP/s (int8)",
+                                 "frac": match["int8_tops_search_kernel"] / i8_peak,
+                                 "note": "search kernel per GPU; peak = 2 x bf16 dense " + peaks["source"]}
+            line["match"] = match
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,8 @@ def load_library():
     lib.bsfm_match_fetch.restype = c.c_int
     lib.bsfm_match_result_dev.argtypes = [c.c_void_p, c.POINTER(c.c_void_p), i64p, c.POINTER(c.c_void_p), i64p]
     lib.bsfm_match_result_dev.restype = c.c_int
+    lib.bsfm_match_copy_result_dev.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.bsfm_match_copy_result_dev.restype = c.c_int
     lib.bsfm_match_shard_pairs.argtypes = [c.c_void_p]
     lib.bsfm_match_shard_pairs.restype = c.c_int64
     lib.bsfm_match_last_timing.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.POINTER(c.c_int)]

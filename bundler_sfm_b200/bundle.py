@@ -147,3 +147,48 @@ def smoke(loader):
     assert abs(r_gpu - r_ref) <= 1e-5, (r_gpu, r_ref)
     assert int(got["info"][5]) == int(ref["info"][5]) and int(got["info"][6]) == int(ref["info"][6])
     print(f"[smoke] BA ok: {int(got['info'][5])} LM iterations, RMSE {r_gpu:.6f} (oracle {r_ref:.6f})")
+
+
+class SfmModel(ctypes.Structure):
+    """== bsfm_sfm_model_t (include/bsfm_b200_ba.h)"""
+    _fields_ = [("est_focal_length", ctypes.c_int), ("undistort", ctypes.c_int), ("explicit_camera_centers", ctypes.c_int),
+                ("f_scale", ctypes.c_double), ("k_scale", ctypes.c_double),
+                ("R_init", ctypes.c_void_p), ("f_fixed", ctypes.c_void_p)]
+
+
+def pack_params(scene, est_focal_length=1, undistort=1, f_scale=0.001, k_scale=5.0):
+    """run_sfm's parameter packing (lib/sfm-driver/sfm.c:652-703) in numpy -> p (m*cnp + 3n doubles)"""
+    m, n = len(scene["f"]), scene["pts"].shape[0]
+    cnp = 6 + (1 if est_focal_length else 0) + (2 if undistort else 0)
+    a = np.zeros((m, cnp))
+    a[:, 0:3] = scene["c"]
+    c = 6
+    if est_focal_length:
+        a[:, 6] = scene["f"] * f_scale
+        c = 7
+    if undistort:
+        a[:, c:c + 2] = scene["k"] * k_scale
+    return np.concatenate([a.reshape(-1), np.asarray(scene["pts"], float).reshape(-1)]), cnp
+
+
+def levmar_model(n, m, vmask_ptr, p_ptr, x_ptr, cnp, R_init, f_fixed, est_focal_length=1, undistort=1,
+                 explicit_camera_centers=1, eps2=1e-12, itmax=150, verbose=0, jac_mode=0):
+    """bsfm_sba_motstr_levmar_model with raw (host or DEVICE) pointers for vmask / p / x.
+    Returns (iterations, info[10])."""
+    lib = load_library()
+    fn = lib.bsfm_sba_motstr_levmar_model
+    c = ctypes
+    fn.argtypes = [c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int,
+                   c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_void_p, c.c_int, c.c_void_p,
+                   c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    fn.restype = c.c_int
+    R_init = np.ascontiguousarray(R_init, dtype=np.float64)
+    f_fixed = np.ascontiguousarray(f_fixed, dtype=np.float64)
+    model = SfmModel(est_focal_length, undistort, explicit_camera_centers, 0.001, 5.0, R_init.ctypes.data, f_fixed.ctypes.data)
+    opts = np.array([1.0e-3, 1.0e-10, eps2, 1.0e-12, 0.0, 4.0e-2])     # sfm.c:705-714
+    info = np.zeros(10)
+    rc = fn(n, m, 0, vmask_ptr, p_ptr, cnp, 3, x_ptr, None, 2, ctypes.addressof(model), jac_mode, itmax, verbose,
+            opts.ctypes.data, info.ctypes.data, 0, None, 0, None, None, None, None, None)
+    if rc < -1:
+        check(rc, "bsfm_sba_motstr_levmar_model")
+    return rc, info

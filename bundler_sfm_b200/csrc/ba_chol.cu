@@ -143,32 +143,82 @@ __global__ void __launch_bounds__(256) chol_syrk_kernel(double *A, int ld, int n
     }
 }
 
-// ---- back substitution L^T x = y (y = row n of A), single CTA --------------------------------------
-__global__ void __launch_bounds__(1024) chol_backsolve_kernel(double *A, int ld, int n, const double *Linv_all, double *x)
+// ---- small systems: whole block-column panel factorised by ONE CTA in shared memory ---------------
+// rows [k0, nrows) x cols [k0, k0+nb): potf2 of the diagonal block fused with the TRSM of every row
+// below it (right-looking, unblocked inside the panel).  Used when the panel fits in shared memory.
+constexpr int PANEL_LD = NB + 1;
+__global__ void __launch_bounds__(1024) chol_panel_smem_kernel(double *A, int ld, int nrows, int k0, int nb, Scalars *sc)
 {
-    __shared__ double xk[NB];
+    extern __shared__ double Pn[];   // [(nrows-k0)][PANEL_LD]
+    __shared__ double djj_s;
+    __shared__ int fail;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nr = nrows - k0;
+    if (tid == 0) fail = 0;
+    for (int q = tid; q < nr * nb; q += nt) {
+        const int r = q / nb, c = q % nb;
+        Pn[r * PANEL_LD + c] = (r >= nb || c <= r) ? A[(size_t) (k0 + r) * ld + (k0 + c)] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; j++) {
+        if (tid == 0) {
+            const double d = Pn[j * PANEL_LD + j];
+            if (!(d > 0.0) || !isfinite(d)) { fail = 1; djj_s = 1.0; }
+            else djj_s = sqrt(d);
+            Pn[j * PANEL_LD + j] = djj_s;
+        }
+        __syncthreads();
+        const double djj = djj_s;
+        for (int r = j + 1 + tid; r < nr; r += nt) Pn[r * PANEL_LD + j] = Pn[r * PANEL_LD + j] / djj;
+        __syncthreads();
+        const int ncols = nb - j - 1;
+        if (ncols > 0) {
+            const int total = (nr - j - 1) * ncols;
+            for (int q = tid; q < total; q += nt) {
+                const int r = j + 1 + q / ncols, c = j + 1 + q % ncols;
+                if (c <= r) Pn[r * PANEL_LD + c] = fma(-Pn[r * PANEL_LD + j], Pn[c * PANEL_LD + j], Pn[r * PANEL_LD + c]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = tid; q < nr * nb; q += nt) {
+        const int r = q / nb, c = q % nb;
+        if (r >= nb || c <= r) A[(size_t) (k0 + r) * ld + (k0 + c)] = Pn[r * PANEL_LD + c];
+    }
+    if (tid == 0 && fail) sc->chol_fail = 1;
+}
+
+// ---- back substitution L^T x = y (y = row n of A), single CTA, row-oriented -----------------------
+// thread c owns y_c (columns strided over the CTA); rows are consumed from the last to the first:
+// x_i = y_i / L_ii, then y_c -= L_ic x_i for c < i (row i of L is contiguous => coalesced).
+constexpr int BS_COLS = 9;   // columns per thread: supports n <= 9216 with 1024 threads
+__global__ void __launch_bounds__(1024) chol_backsolve_kernel(const double *A, int ld, int n, double *x)
+{
+    __shared__ double xi_s[2];
     const int tid = threadIdx.x;
-    double *y = A + (size_t) n * ld;   // RHS row, overwritten progressively
-    const int nblk = (n + NB - 1) / NB;
-    for (int kb = nblk - 1; kb >= 0; kb--) {
-        const int k0 = kb * NB, nb = min(NB, n - k0);
-        const double *Li = Linv_all + (size_t) kb * NB * NB;
-        // x_k = L_kk^-T y_k : x[c] = sum_{r>=c} Linv[r][c] y[r]
-        if (tid < NB) {
-            double s = 0.0;
-            if (tid < nb)
-                for (int r = tid; r < nb; r++) s += Li[r * NB + tid] * y[k0 + r];
-            xk[tid] = s;
-            if (tid < nb) x[k0 + tid] = s;
+    const double *yrow = A + (size_t) n * ld;
+    double y[BS_COLS];
+#pragma unroll
+    for (int q = 0; q < BS_COLS; q++) { const int c = tid + q * 1024; y[q] = (c < n) ? yrow[c] : 0.0; }
+    for (int i = n - 1; i >= 0; i--) {
+        const double *Li = A + (size_t) i * ld;
+        // issue this row's loads before the dependent broadcast
+        double l[BS_COLS];
+#pragma unroll
+        for (int q = 0; q < BS_COLS; q++) { const int c = tid + q * 1024; l[q] = (c < i) ? Li[c] : 0.0; }
+        const int owner = i & 1023, oq = i >> 10;
+        if (tid == owner) {
+            double yi = 0.0;
+#pragma unroll
+            for (int q = 0; q < BS_COLS; q++) if (q == oq) yi = y[q];
+            const double xi = yi / Li[i];
+            xi_s[i & 1] = xi;
+            x[i] = xi;
         }
         __syncthreads();
-        // y[0:k0] -= L[k0:k0+nb, 0:k0]^T x_k
-        for (int c = tid; c < k0; c += 1024) {
-            double s = 0.0;
-            for (int r = 0; r < nb; r++) s += A[(size_t) (k0 + r) * ld + c] * xk[r];
-            y[c] -= s;
-        }
-        __syncthreads();
+        const double xi = xi_s[i & 1];
+#pragma unroll
+        for (int q = 0; q < BS_COLS; q++) y[q] = fma(-l[q], xi, y[q]);
     }
 }
 
@@ -177,6 +227,13 @@ __global__ void __launch_bounds__(1024) chol_backsolve_kernel(double *A, int ld,
 int chol_solve(cudaStream_t st, double *A, int n, double *linv_ws, double *x, Scalars *sc)
 {
     const int ld = n, nrows = n + 1;
+    if (n > 1024 * BS_COLS) { set_error("reduced camera system of dimension %d exceeds the supported %d", n, 1024 * BS_COLS); return BSFM_ERR_UNSUPPORTED; }
+    const size_t panel_bytes = (size_t) nrows * PANEL_LD * sizeof(double);
+    const bool small = panel_bytes <= 200 * 1024;
+    if (small) {
+        static bool attr = false;
+        if (!attr) { BSFM_CUDA_TRY(cudaFuncSetAttribute(chol_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    }
     const int NBO = (n > 2048) ? 256 : NB;
     const int BT = (n <= 1024) ? 32 : (n <= 4096 ? 64 : 128);
     auto syrk = [&](int cb, int ce, int kb, int ke) -> int {
@@ -194,13 +251,20 @@ int chol_solve(cudaStream_t st, double *A, int n, double *linv_ws, double *x, Sc
         const int K1 = min(n, K0 + NBO);
         for (int k0 = K0; k0 < K1; k0 += NB) {
             const int nb = min(NB, n - k0);
-            double *Li = linv_ws + (size_t) (k0 / NB) * NB * NB;
-            chol_diag_kernel<<<1, 256, 0, st>>>(A, ld, k0, nb, Li, sc);
-            BSFM_KERNEL_CHECK();
-            const int rows_below = nrows - (k0 + nb);
-            if (rows_below > 0) {
-                chol_trsm_kernel<<<(rows_below + 63) / 64, 256, 0, st>>>(A, ld, nrows, k0, nb, Li);
+            if (small) {
+                const int nr = nrows - k0;
+                const int threads = nr * nb >= 8192 ? 1024 : (nr * nb >= 2048 ? 512 : 256);
+                chol_panel_smem_kernel<<<1, threads, (size_t) nr * PANEL_LD * sizeof(double), st>>>(A, ld, nrows, k0, nb, sc);
                 BSFM_KERNEL_CHECK();
+            } else {
+                double *Li = linv_ws + (size_t) (k0 / NB) * NB * NB;
+                chol_diag_kernel<<<1, 256, 0, st>>>(A, ld, k0, nb, Li, sc);
+                BSFM_KERNEL_CHECK();
+                const int rows_below = nrows - (k0 + nb);
+                if (rows_below > 0) {
+                    chol_trsm_kernel<<<(rows_below + 63) / 64, 256, 0, st>>>(A, ld, nrows, k0, nb, Li);
+                    BSFM_KERNEL_CHECK();
+                }
             }
             // inner update restricted to the columns of the outer panel
             int rc = syrk(k0 + nb, K1, k0, k0 + nb);
@@ -214,7 +278,7 @@ int chol_solve(cudaStream_t st, double *A, int n, double *linv_ws, double *x, Sc
             // RHS row (row n) against columns >= K1 is part of the tiles (nrows = n + 1)
         }
     }
-    chol_backsolve_kernel<<<1, 1024, 0, st>>>(A, ld, n, linv_ws, x);
+    chol_backsolve_kernel<<<1, 1024, 0, st>>>(A, ld, n, x);
     BSFM_KERNEL_CHECK();
     return BSFM_OK;
 }

@@ -533,10 +533,11 @@ __global__ void penalty_kernel(Problem P, const double *p)
 // ------------------------------------------------------------------------------------------------
 // K4: (V_i + mu I)^-1, 3x3 SPD via Cholesky (reference: LAPACK dsytrf/dsytri, sba_lapack.c:1053-1140)
 // ------------------------------------------------------------------------------------------------
-__global__ void vinv_kernel(Problem P, double mu)
+__global__ void vinv_kernel(Problem P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    const double mu = *P.mu;
     const double *V = P.V + (size_t) i * 9;
     const double a00 = V[0] + mu, a01 = V[1], a02 = V[2], a11 = V[4] + mu, a12 = V[5], a22 = V[8] + mu;
     // cofactor inverse of a symmetric 3x3 (exact formula; the matrix is SPD for mu > 0)
@@ -557,85 +558,117 @@ __global__ void vinv_kernel(Problem P, double mu)
 
 // ------------------------------------------------------------------------------------------------
 // K5: S_jk = delta_jk (U_j + mu I) - sum_i Y_ij W_ik^T,  E_j = ea_j - sum_i Y_ij eb_i,
-// Y_ij = W_ij (V_i + mu I)^-1.   One warp per upper block (j <= k); tuples are in ascending point
-// order (the reference's summation order, sba_levmar.c:1219-1260).  Lane l < 27 owns Y element
-// (l/3, l%3); the 81 block entries are spread 3 per lane and fed by shuffles.
+// Y_ij = W_ij (V_i + mu I)^-1   (sba_levmar.c:1195-1338).
+// Upper blocks (j <= k) only; every block's tuple list (ascending point = the reference's summation
+// order) is cut into chunks of SCHUR_CHUNK tuples.  Pass A: one warp per chunk accumulates a partial
+// 9x9 (+ 9 for E on diagonal blocks).  Pass B: one warp per block adds its chunks in order and writes
+// S (both triangles) and E.  Fixed shapes and orders => bitwise reproducible.
+// Lane l < 27 owns Y element (l/3, l%3); the 81 block entries are spread 3 per lane, fed by shuffles.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) schur_kernel(Problem P, double mu)
+__global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
 {
-    const int wglob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (wglob >= P.nblocks) return;
+    if (c >= P.nchunks) return;
     const int cnp = P.M.cnp, m = P.m;
-    const uint32_t key = P.blk_key[wglob];
-    const int j = (int) (key / (uint32_t) m), k = (int) (key % (uint32_t) m);
-    const int nY = cnp * 3;
-    const int yr = lane / 3, yc = lane % 3;     // Y element of this lane (valid when lane < nY)
-    // block entries owned by this lane: q = lane, lane+32, lane+64 (< cnp*cnp), entry (q / cnp, q % cnp)
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, accE = 0.0;
+    // block of this chunk: last b with chunk_off[b] <= c
+    int lo = 0, hi = P.nblocks - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (P.chunk_off[mid] <= c) lo = mid; else hi = mid - 1; }
+    const int b = lo;
+    const uint32_t key = P.blk_key[b];
+    const bool diag = (key / (uint32_t) m) == (key % (uint32_t) m);
+    const int t0 = P.blk_start[b] + (c - P.chunk_off[b]) * SCHUR_CHUNK;
+    const int t1 = min(t0 + SCHUR_CHUNK, P.blk_start[b + 1]);
+    const int nY = cnp * 3, nn = cnp * cnp;
+    const int yr = (lane < nY ? lane : 0) / 3, yc = lane % 3;
     const int q0 = lane, q1 = lane + 32, q2 = lane + 64;
-    const int nn = cnp * cnp;
-    const int t0 = P.blk_start[wglob], t1 = P.blk_start[wglob + 1];
+    const int i0 = (q0 < nn ? q0 : 0) / cnp, j0 = (q0 < nn ? q0 : 0) % cnp;
+    const int i1 = (q1 < nn ? q1 : 0) / cnp, j1 = (q1 < nn ? q1 : 0) % cnp;
+    const int i2 = (q2 < nn ? q2 : 0) / cnp, j2 = (q2 < nn ? q2 : 0) % cnp;
+    const int er = lane < cnp ? lane : 0;
     const double *eb = P.eab + (size_t) m * cnp;
-    for (int t = t0; t < t1; t++) {
-        const int2 tp = P.tuples[t];
-        const int i = P.obs_pt[tp.x];
-        const double *Wa = P.W + (size_t) tp.x * nY;
-        const double *Wb = P.W + (size_t) tp.y * nY;
-        const double *Vi = P.Vinv + (size_t) i * 9;
-        double y = 0.0, wb = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, accE = 0.0;
+
+    // software pipeline: operands of tuple t+1 are in flight while tuple t is reduced
+    double wa0 = 0, wa1 = 0, wa2 = 0, v0 = 0, v1 = 0, v2 = 0, wb = 0, ebv = 0;
+    auto load = [&](int t) {
+        const int4 tp = P.tuples[t];
         if (lane < nY) {
-            // Y[yr][yc] = sum_c Wa[yr][c] * Vinv[c][yc]   (sba_levmar.c:1206-1214)
-            double s = 0.0;
-            s += Wa[yr * 3 + 0] * Vi[0 * 3 + yc];
-            s += Wa[yr * 3 + 1] * Vi[1 * 3 + yc];
-            s += Wa[yr * 3 + 2] * Vi[2 * 3 + yc];
-            y = s;
-            wb = Wb[lane];
+            const double *Wa = P.W + (size_t) tp.x * nY + yr * 3;
+            const double *Vi = P.Vinv + (size_t) tp.z * 9 + yc;
+            wa0 = Wa[0]; wa1 = Wa[1]; wa2 = Wa[2];
+            v0 = Vi[0]; v1 = Vi[3]; v2 = Vi[6];
+            wb = P.W[(size_t) tp.y * nY + lane];
         }
+        if (diag && lane < 3) ebv = eb[(size_t) tp.z * 3 + lane];
+    };
+    if (t0 < t1) load(t0);
+    for (int t = t0; t < t1; t++) {
+        // Y[yr][yc] = sum_c Wa[yr][c] * Vinv[c][yc]   (sba_levmar.c:1206-1214)
+        double y = 0.0;
+        y += wa0 * v0; y += wa1 * v1; y += wa2 * v2;
+        const double wbc = wb, ebc = ebv;
+        if (t + 1 < t1) load(t + 1);
         // YWt[ii][jj] += sum_l Y[ii][l] * Wb[jj][l]      (sba_levmar.c:1262-1275)
-#pragma unroll
-        for (int rep = 0; rep < 3; rep++) {
-            const int q = rep == 0 ? q0 : (rep == 1 ? q1 : q2);
-            const int qq = q < nn ? q : 0;
-            const int ii = qq / cnp, jj = qq % cnp;
+        {
             double s = 0.0;
 #pragma unroll
-            for (int l = 0; l < 3; l++) {
-                const double yv = __shfl_sync(0xffffffffu, y, ii * 3 + l);
-                const double wv = __shfl_sync(0xffffffffu, wb, jj * 3 + l);
-                s += yv * wv;
-            }
-            if (rep == 0) acc0 += s; else if (rep == 1) acc1 += s; else acc2 += s;
+            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, i0 * 3 + l) * __shfl_sync(0xffffffffu, wbc, j0 * 3 + l);
+            acc0 += s;
+            s = 0.0;
+#pragma unroll
+            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, i1 * 3 + l) * __shfl_sync(0xffffffffu, wbc, j1 * 3 + l);
+            acc1 += s;
+            s = 0.0;
+#pragma unroll
+            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, i2 * 3 + l) * __shfl_sync(0xffffffffu, wbc, j2 * 3 + l);
+            acc2 += s;
         }
-        if (j == k) {
-            // E_j partial: sum_i Y_ij eb_i (sba_levmar.c:1318-1333); lane ii < cnp owns row ii
-            const double ebv = (lane < 3) ? eb[(size_t) i * 3 + lane] : 0.0;
+        if (diag) {   // E_j partial: sum_i Y_ij eb_i (sba_levmar.c:1318-1333); lane ii < cnp owns row ii
             double s = 0.0;
 #pragma unroll
-            for (int l = 0; l < 3; l++) {
-                const double yv = __shfl_sync(0xffffffffu, y, (lane < cnp ? lane : 0) * 3 + l);
-                const double ev = __shfl_sync(0xffffffffu, ebv, l);
-                s += yv * ev;
-            }
+            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, er * 3 + l) * __shfl_sync(0xffffffffu, ebc, l);
             accE += s;
         }
+    }
+    double *out = P.schur_part + (size_t) c * SCHUR_PART_STRIDE;
+    if (q0 < nn) out[q0] = acc0;
+    if (q1 < nn) out[q1] = acc1;
+    if (q2 < nn) out[q2] = acc2;
+    if (diag && lane < cnp) out[81 + lane] = accE;
+}
+
+__global__ void __launch_bounds__(128) schur_final_kernel(Problem P)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= P.nblocks) return;
+    const int cnp = P.M.cnp, m = P.m, nn = cnp * cnp;
+    const double mu = *P.mu;
+    const uint32_t key = P.blk_key[b];
+    const int j = (int) (key / (uint32_t) m), k = (int) (key % (uint32_t) m);
+    const int c0 = P.chunk_off[b], c1 = P.chunk_off[b + 1];
+    double acc[3] = {0.0, 0.0, 0.0}, accE = 0.0;
+    for (int c = c0; c < c1; c++) {
+        const double *part = P.schur_part + (size_t) c * SCHUR_PART_STRIDE;
+#pragma unroll
+        for (int rep = 0; rep < 3; rep++) { const int q = lane + 32 * rep; if (q < nn) acc[rep] += part[q]; }
+        if (j == k && lane < cnp) accE += part[81 + lane];
     }
     const int Sdim = P.Sdim;
     const int jr = (j - P.mcon) * cnp, kr = (k - P.mcon) * cnp;
 #pragma unroll
     for (int rep = 0; rep < 3; rep++) {
-        const int q = rep == 0 ? q0 : (rep == 1 ? q1 : q2);
+        const int q = lane + 32 * rep;
         if (q < nn) {
             const int ii = q / cnp, jj = q % cnp;
-            const double a = rep == 0 ? acc0 : (rep == 1 ? acc1 : acc2);
             double v;
             if (j == k) {
                 double u = P.U[(size_t) j * nn + ii * cnp + jj];
                 if (ii == jj) u += mu;
-                v = u - a;
+                v = u - acc[rep];
             } else {
-                v = -a;
+                v = -acc[rep];
             }
             P.S[(size_t) (jr + ii) * Sdim + (kr + jj)] = v;
             if (j != k) P.S[(size_t) (kr + jj) * Sdim + (jr + ii)] = v;
@@ -693,9 +726,10 @@ __global__ void backsub_kernel(Problem P, const double *da)
 // ------------------------------------------------------------------------------------------------
 // K8b: pdp = p + dp, ||dp||^2, dL = sum dp (mu dp + J^T e)   (sba_levmar.c:1443-1447, 1524-1525)
 // ------------------------------------------------------------------------------------------------
-__global__ void update_kernel(Problem P, const double *p, double *pdp, double mu)
+__global__ void update_kernel(Problem P, const double *p, double *pdp)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const double mu = *P.mu;
     double d2 = 0.0, dl = 0.0;
     if (q < P.nvars) {
         const double d = P.dp[q];
@@ -723,7 +757,7 @@ __global__ void vmask_count_kernel(const char *vmask, int n, int m, int *row_cou
     if (lane == 0) row_count[i] = c;
 }
 
-__global__ void vmask_fill_kernel(const char *vmask, int n, int m, const int *rowptr, int *obs_cam, int *obs_pt, int *tuple_count)
+__global__ void vmask_fill_kernel(const char *vmask, int n, int m, const int *rowptr, int *obs_cam, int *obs_pt)
 {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -738,10 +772,6 @@ __global__ void vmask_fill_kernel(const char *vmask, int n, int m, const int *ro
             obs_cam[q] = j; obs_pt[q] = i;
         }
         pos += __popc(ball);
-    }
-    if (lane == 0 && tuple_count) {
-        const int L = rowptr[i + 1] - rowptr[i];
-        tuple_count[i] = L * (L + 1) / 2;
     }
 }
 
@@ -772,6 +802,20 @@ __global__ void tuple_fill_kernel(int n, int m, int mcon, const int *rowptr, con
             pos++;
         }
     }
+}
+
+// sorted (obs_a, obs_b) -> (obs_a, obs_b, point, 0)
+__global__ void tuple_expand_kernel(const int2 *in, const int *obs_pt, int4 *out, int count)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < count) { const int2 v = in[q]; out[q] = make_int4(v.x, v.y, obs_pt[v.x], 0); }
+}
+
+__global__ void chunk_count_kernel(const int *blk_cnt, int nblocks, int *chunk_cnt)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblocks) chunk_cnt[b] = (blk_cnt[b] + SCHUR_CHUNK - 1) / SCHUR_CHUNK;
+    else if (b == nblocks) chunk_cnt[b] = 0;
 }
 
 __global__ void iota_kernel(int *v, int count)

@@ -14,6 +14,8 @@ namespace ba {
 constexpr int MAX_CNP = 9;
 constexpr int PNP = 3;
 constexpr int MNP = 2;
+constexpr int SCHUR_CHUNK = 32;        // tuples per partial-sum warp
+constexpr int SCHUR_PART_STRIDE = 96;  // doubles per partial (81 block entries + 9 E + pad)
 
 struct Model {
     int cnp, est_focal, undistort, explicit_centers;
@@ -51,7 +53,10 @@ struct Problem {
     int nblocks;
     const uint32_t *blk_key;   // j*m + k
     const int *blk_start;      // nblocks+1
-    const int2 *tuples;        // (obs_a, obs_b)
+    const int4 *tuples;        // (obs_a, obs_b, point, 0)
+    int nchunks;
+    const int *chunk_off;      // nblocks+1: first chunk of every block
+    double *schur_part;        // nchunks * SCHUR_PART_STRIDE
     // data
     const double *x;       // 2*nvis measurements
     const double *R_init;  // m*9
@@ -78,6 +83,7 @@ struct Problem {
     double *partial;  // reduction scratch
     unsigned int *ticket;  // last-block counters
     Scalars *sc;      // device scalars
+    const double *mu; // damping term of the current try (device scalar, written by the host)
 };
 
 }  // namespace ba

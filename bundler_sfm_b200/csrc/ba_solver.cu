@@ -26,11 +26,14 @@ __global__ void v_kernel(Problem, const double *, const double *);
 __global__ void u_kernel(Problem, const double *, const double *);
 __global__ void grad_stats_kernel(Problem, const double *);
 __global__ void penalty_kernel(Problem, const double *);
-__global__ void vinv_kernel(Problem, double);
-__global__ void schur_kernel(Problem, double);
+__global__ void vinv_kernel(Problem);
+__global__ void schur_partial_kernel(Problem);
+__global__ void schur_final_kernel(Problem);
+__global__ void tuple_expand_kernel(const int2 *, const int *, int4 *, int);
+__global__ void chunk_count_kernel(const int *, int, int *);
 __global__ void zero_kernel(double *, size_t);
 __global__ void backsub_kernel(Problem, const double *);
-__global__ void update_kernel(Problem, const double *, double *, double);
+__global__ void update_kernel(Problem, const double *, double *);
 __global__ void vmask_count_kernel(const char *, int, int, int *);
 __global__ void vmask_fill_kernel(const char *, int, int, const int *, int *, int *);
 __global__ void tuple_count_kernel(int, int, const int *, const int *, int *);
@@ -165,7 +168,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     TRY(D.alloc(&d_vmask, (size_t) n * m));
     TRY(D.alloc(&d_rowcnt, (size_t) n + 1));
     TRY(D.alloc(&d_rowptr, (size_t) n + 1));
-    BSFM_CUDA_TRY(cudaMemcpyAsync(d_vmask, vmask, (size_t) n * m, cudaMemcpyHostToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_vmask, vmask, (size_t) n * m, cudaMemcpyDefault, st));   // host or device pointer (UVA)
     BSFM_CUDA_TRY(cudaMemsetAsync(d_rowcnt, 0, ((size_t) n + 1) * sizeof(int), st));
     vmask_count_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_vmask, n, m, d_rowcnt);
     BSFM_KERNEL_CHECK();
@@ -201,7 +204,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     BSFM_KERNEL_CHECK();
     double *d_x;
     TRY(D.alloc(&d_x, (size_t) nobs));
-    BSFM_CUDA_TRY(cudaMemcpyAsync(d_x, x, (size_t) nobs * sizeof(double), cudaMemcpyHostToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_x, x, (size_t) nobs * sizeof(double), cudaMemcpyDefault, st));
     // camera-major permutation: stable sort of observation ids by camera
     TRY(D.alloc(&d_key_a, (size_t) nvis)); TRY(D.alloc(&d_key_b, (size_t) nvis));
     cast_u32_kernel<<<(nvis + 255) / 256, 256, 0, st>>>(d_obs_cam, d_key_a, nvis);
@@ -270,7 +273,28 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         count_launch(2);
     }
     P.rowptr = d_rowptr; P.obs_cam = d_obs_cam; P.obs_pt = d_obs_pt; P.cam_ptr = d_cam_ptr; P.cam_obs = d_cam_obs;
-    P.nblocks = nblocks; P.blk_key = d_blk_key; P.blk_start = d_blk_start; P.tuples = (const int2 *) d_tval_b;
+    // chunk list (SCHUR_CHUNK tuples per partial-sum warp) + (obs_a, obs_b, point) tuples
+    int *d_chunk_cnt, *d_chunk_off;
+    int4 *d_tuples4;
+    TRY(D.alloc(&d_chunk_cnt, (size_t) nblocks + 1)); TRY(D.alloc(&d_chunk_off, (size_t) nblocks + 1));
+    TRY(D.alloc(&d_tuples4, (size_t) ntuples));
+    chunk_count_kernel<<<(nblocks + 1 + 255) / 256, 256, 0, st>>>(d_blk_cnt, nblocks, d_chunk_cnt);
+    BSFM_KERNEL_CHECK();
+    {
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, d_chunk_cnt, d_chunk_off, nblocks + 1, st);
+        TRY(ensure_cub(need));
+        cub::DeviceScan::ExclusiveSum(d_cub, need, d_chunk_cnt, d_chunk_off, nblocks + 1, st);
+        count_launch(2);
+    }
+    tuple_expand_kernel<<<(ntuples + 255) / 256, 256, 0, st>>>((const int2 *) d_tval_b, d_obs_pt, d_tuples4, ntuples);
+    BSFM_KERNEL_CHECK();
+    int nchunks = 0;
+    BSFM_CUDA_TRY(cudaMemcpyAsync(&nchunks, d_chunk_off + nblocks, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(st));
+    P.nblocks = nblocks; P.blk_key = d_blk_key; P.blk_start = d_blk_start; P.tuples = d_tuples4;
+    P.nchunks = nchunks; P.chunk_off = d_chunk_off;
+    TRY(D.alloc(&P.schur_part, (size_t) nchunks * SCHUR_PART_STRIDE));
     P.x = d_x;
 
     // model + constraints
@@ -333,10 +357,15 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     BSFM_CUDA_TRY(cudaMemsetAsync(P.ticket, 0, 4 * sizeof(unsigned int), st));
     TRY(D.alloc(&P.sc, 1));
     BSFM_CUDA_TRY(cudaMemsetAsync(P.sc, 0, sizeof(Scalars), st));
+    double *d_mu, *h_mu = nullptr;
+    TRY(D.alloc(&d_mu, 1));
+    P.mu = d_mu;
+    BSFM_CUDA_TRY(cudaMallocHost(&h_mu, sizeof(double)));
+    struct HostGuard2 { void *p; ~HostGuard2() { cudaFreeHost(p); } } hguard2{h_mu};
     Scalars *h_sc = nullptr;
     BSFM_CUDA_TRY(cudaMallocHost(&h_sc, sizeof(Scalars)));
     struct HostGuard { void *p; ~HostGuard() { cudaFreeHost(p); } } hguard{h_sc};
-    BSFM_CUDA_TRY(cudaMemcpyAsync(d_p, p, (size_t) P.nvars * sizeof(double), cudaMemcpyHostToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_p, p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));
     PT.end();
 
     auto read_scalars = [&]() -> int {
@@ -360,6 +389,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     double mu = 0.0, eab_inf = 0.0, p_eL2, pdp_eL2, p_L2 = 0.0, dp_L2 = DBL_MAX, dF, dL, init_p_eL2, max_diag = DBL_MIN, pen = 0.0;
     int nu = 2, nu2, stop = 0, nfev = 0, njev = 0, nlss = 0, itno = 0;
     const bool any_constraints = use_constraints || use_point_constraints;
+    const bool s_dense = (int64_t) nblocks == (int64_t) (m - mcon) * (m - mcon + 1) / 2;   // every block written by the Schur pass
 
     PT.begin(4);
     TRY(launch_residual(d_p, d_camR_a, d_e, nullptr, 0.0)); nfev = 1;
@@ -393,12 +423,18 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
 
         while (1) {   // damping loop :1131
             BSFM_CUDA_TRY(cudaMemsetAsync(&P.sc->singular_v, 0, 3 * sizeof(int), st));
+            *h_mu = mu;
+            BSFM_CUDA_TRY(cudaMemcpyAsync(d_mu, h_mu, sizeof(double), cudaMemcpyHostToDevice, st));
             PT.begin(2);
-            vinv_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, mu);
+            vinv_kernel<<<(n + 255) / 256, 256, 0, st>>>(P);
             BSFM_KERNEL_CHECK();
-            zero_kernel<<<std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, 0, st>>>(P.S, (size_t) Sdim * Sdim);
+            if (!s_dense) {   // camera pairs without a common point keep S_jk = 0
+                zero_kernel<<<std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, 0, st>>>(P.S, (size_t) Sdim * Sdim);
+                BSFM_KERNEL_CHECK();
+            }
+            schur_partial_kernel<<<(nchunks * 32 + 127) / 128, 128, 0, st>>>(P);
             BSFM_KERNEL_CHECK();
-            schur_kernel<<<(nblocks * 32 + 127) / 128, 128, 0, st>>>(P, mu);
+            schur_final_kernel<<<(nblocks * 32 + 127) / 128, 128, 0, st>>>(P);
             BSFM_KERNEL_CHECK();
             PT.end();
             PT.begin(3);
@@ -407,7 +443,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
             PT.begin(4);
             backsub_kernel<<<(std::max(n, m * cnp) + 127) / 128, 128, 0, st>>>(P, d_da);
             BSFM_KERNEL_CHECK();
-            update_kernel<<<red_blocks_var, 256, 0, st>>>(P, d_p, d_pdp, mu);
+            update_kernel<<<red_blocks_var, 256, 0, st>>>(P, d_p, d_pdp);
             BSFM_KERNEL_CHECK();
             TRY(launch_residual(d_pdp, d_camR_b, d_enew, d_e, eps5));
             PT.end();
@@ -472,7 +508,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     }
     if (itno >= itmax) stop = 3;
 
-    BSFM_CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t) P.nvars * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));
     BSFM_CUDA_TRY(cudaEventRecord(ev_end, st));
     BSFM_CUDA_TRY(cudaStreamSynchronize(st));
     if (info) {   // :2028-2049

@@ -229,6 +229,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     MatchParams P;
     P.keys_sw = db->d_keys_sw; P.norms = db->d_norms; P.run_imgs = d_run; P.num_run_imgs = K;
     P.ratio_sq = ratio * ratio;
+    P.neg2 = -2;
     P.cand = (int32_t *) (S + o_cand); P.cand_cap = (int32_t) cap;
     P.match_slot = (uint32_t *) (S + o_slot_a); P.match_idx2 = (int32_t *) (S + o_idx_a); P.match_cap = (int32_t) cap;
     P.counters = (int32_t *) (S + o_cnt);
@@ -368,6 +369,18 @@ int bsfm_match_result_dev(bsfm_keydb *db, const int32_t **pair_counts_dev, int64
     if (num_pairs) *num_pairs = db->shard_pairs;
     if (matches_dev) *matches_dev = db->d_matches;
     if (num_matches) *num_matches = db->total_matches;
+    return BSFM_OK;
+}
+
+int bsfm_match_copy_result_dev(bsfm_keydb *db, int32_t *pair_counts_dst_dev, int32_t *matches_dst_dev)
+{
+    clear_error();
+    if (!db) { set_error("bsfm_match_copy_result_dev: null db"); return BSFM_ERR_ARG; }
+    if (db->shard_pairs > 0 && pair_counts_dst_dev)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(pair_counts_dst_dev, db->d_pair_counts, (size_t) db->shard_pairs * sizeof(int32_t), cudaMemcpyDeviceToDevice, db->stream));
+    if (db->total_matches > 0 && matches_dst_dev)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(matches_dst_dev, db->d_matches, (size_t) db->total_matches * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, db->stream));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
     return BSFM_OK;
 }
 

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(256) match_dp4a_kernel(MatchParams P)
 // tcgen05 kernel: persistent, warp-specialised.
 //   warp 0      : TMA producer (cp.async.bulk, one 16 KB query tile per unit, 32 KB database tiles)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::i8, M128 N256 K32 x4)
-//   warps 2..5  : epilogue, one TMEM lane quadrant each (thread == query row)
+//   warps 2..9  : epilogue; warp w reads TMEM lane quadrant w%4 (thread == query row) and column
+//                 half (w-2)/4 of every 256-column tile; the two halves of a row are merged at unit end
 // Accumulators double-buffered in TMEM (2 x 256 columns); shared-memory database ring of 4 stages.
 // Epilogue per element: t = |p|^2 - 2*dot (IMAD), chunk minimum (VIMNMX3 tree).  Per 32-column
 // chunk the row keeps (m1 = smallest chunk-min, s2 = second smallest chunk-min, bchunk).  d0 is
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             mbar_init(bar_a_full + 8 * s, 1);
             mbar_init(bar_a_empty + 8 * s, 1);
             mbar_init(bar_t_full + 8 * s, 1);
-            mbar_init(bar_t_empty + 8 * s, 128);
+            mbar_init(bar_t_empty + 8 * s, TC_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -349,10 +350,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             }
         }
     } else {
-        // ===================== epilogue (4 warps) =====================
+        // ===================== epilogue (8 warps) =====================
         const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;        // which 128 columns of each 256-column tile
         const int row = quad * 32 + lane;        // query row inside the unit
-        const int etid = threadIdx.x - 64;       // 0..127
+        const int etid = threadIdx.x - 64;       // 0..255
+        const int neg2 = P.neg2;                 // runtime -2: keeps the multiply-add on the FMA pipe (IMAD)
+        int *xch = reinterpret_cast<int *>(smem + TC_SMEM_XCH);   // [3][128] exchange between column halves
         uint32_t ts = 0, tph = 0;
         for (int u = u_first; u < P.unit_end; u += u_step) {
             const UnitInfo U = decode_unit(P, u);
@@ -360,15 +364,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             int m1 = INT_MAX, s2 = INT_MAX, bchunk = 0;
             for (int t = 0; t < U.ntiles_db; t++) {
                 // stage this tile's 256 database norms in shared memory (buffer = accumulator stage)
-                const int2 nv = *reinterpret_cast<const int2 *>(P.norms + (size_t) U.db_row0 + (size_t) t * TILE_DB + etid * 2);
-                *reinterpret_cast<int2 *>(sN + ts * TILE_DB + etid * 2) = nv;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                sN[ts * TILE_DB + etid] = P.norms[(size_t) U.db_row0 + (size_t) t * TILE_DB + etid];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 mbar_wait(bar_t_full + 8 * ts, tph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + ts * TILE_DB;
-                const int4 *nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB);
+                const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + ts * TILE_DB + half * (TILE_DB / 2);
+                const int4 *nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB + half * (TILE_DB / 2));
 #pragma unroll 1
-                for (int c = 0; c < TILE_DB / CHUNK; c++) {
+                for (int c = 0; c < TILE_DB / CHUNK / 2; c++) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * CHUNK, v);
                     tmem_ld_wait();
@@ -376,15 +379,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         const int4 nb = nb4[c * 8 + q];
-                        const int t0 = nb.x - 2 * (int) v[4 * q + 0];
-                        const int t1 = nb.y - 2 * (int) v[4 * q + 1];
-                        const int t2 = nb.z - 2 * (int) v[4 * q + 2];
+                        // t = |p|^2 - 2 q.p ; three on the FMA pipe (IMAD), one on the ALU pipe (IADD3)
+                        const int t0 = (int) v[4 * q + 0] * neg2 + nb.x;
+                        const int t1 = (int) v[4 * q + 1] * neg2 + nb.y;
+                        const int t2 = (int) v[4 * q + 2] * neg2 + nb.z;
                         const int t3 = nb.w - 2 * (int) v[4 * q + 3];
                         cm = min(cm, min(min(t0, t1), min(t2, t3)));
                     }
                     // (m1, s2) <- two smallest of {m1, s2, cm}
                     const int hi = max(m1, cm);
-                    if (cm < m1) bchunk = t * (TILE_DB / CHUNK) + c;
+                    if (cm < m1) bchunk = t * (TILE_DB / CHUNK) + half * (TILE_DB / CHUNK / 2) + c;
                     m1 = min(m1, cm);
                     s2 = min(s2, hi);
                 }
@@ -392,14 +396,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                 mbar_arrive(bar_t_empty + 8 * ts);
                 ts ^= 1; if (ts == 0) tph ^= 1;
             }
-            // unit finished: provisional ratio test with the upper bound on d1
+            // merge the two column halves of every row (half 1 -> shared memory -> half 0)
+            if (half == 1) { xch[row] = m1; xch[128 + row] = s2; xch[256 + row] = bchunk; }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             bool cand = false;
             int d1u = INT_MAX;
-            if (na < NORM_PAD_HALF) {
-                const int d0 = na + m1;
-                d1u = (s2 >= NORM_PAD_HALF) ? INT_MAX : na + s2;
-                cand = (double) d0 < P.ratio_sq * (double) d1u;
+            if (half == 0) {
+                const int o1 = xch[row], o2 = xch[128 + row], ob = xch[256 + row];
+                const int hi = max(m1, o1);
+                if (o1 < m1) bchunk = ob;
+                m1 = min(m1, o1);
+                s2 = min(min(s2, o2), hi);
+                // unit finished: provisional ratio test with the upper bound on d1
+                if (na < NORM_PAD_HALF) {
+                    const int d0 = na + m1;
+                    d1u = (s2 >= NORM_PAD_HALF) ? INT_MAX : na + s2;
+                    cand = (double) d0 < P.ratio_sq * (double) d1u;
+                }
             }
+            asm volatile("bar.sync 3, 256;" ::: "memory");   // xch may be overwritten by the next unit
             const unsigned ball = __ballot_sync(0xffffffffu, cand);
             if (ball) {
                 int basepos = 0;

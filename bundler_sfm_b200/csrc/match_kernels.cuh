@@ -30,14 +30,17 @@ constexpr int32_t NORM_PAD = 1 << 30;
 constexpr int32_t NORM_PAD_HALF = 1 << 29;
 
 // tensor-core kernel configuration (shared by kernel and launcher)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr int TC_B_STAGES = 4;
 constexpr int TC_A_BYTES = TILE_Q * DESC_BYTES;    // 16384
 constexpr int TC_B_BYTES = TILE_DB * DESC_BYTES;   // 32768
 constexpr int TC_SMEM_A = 0;
 constexpr int TC_SMEM_B = 2 * TC_A_BYTES;
 constexpr int TC_SMEM_N = TC_SMEM_B + TC_B_STAGES * TC_B_BYTES;   // 2 x 256 int32 norms
-constexpr int TC_SMEM_BAR = TC_SMEM_N + 2 * TILE_DB * 4;
+constexpr int TC_SMEM_XCH = TC_SMEM_N + 2 * TILE_DB * 4;              // 3 x 128 int32 half-merge exchange
+constexpr int TC_SMEM_BAR = TC_SMEM_XCH + 3 * 128 * 4;
 constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
 constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 
@@ -63,6 +66,7 @@ struct MatchParams {
     int32_t unit_begin;         // units [unit_begin, unit_end) are processed by this launch
     int32_t unit_end;
     double ratio_sq;            // ratio*ratio evaluated on the host in double (keys2a.cpp:362)
+    int32_t neg2;               // the constant -2 as a runtime value (see the epilogue of match_tc_kernel)
     // candidate list (tensor-core kernel): SoA int32 [6][cand_cap]: slot, qrow, db0, col0, nvalid, d1u
     int32_t *cand;
     int32_t cand_cap;

@@ -103,6 +103,15 @@ class KeyDatabase:
               "bsfm_match_result_dev")
         return ptr_c.value, n_p.value, ptr_m.value, n_m.value
 
+    def result_to_torch(self, device):
+        """(pair_counts, matches) of the last run as torch int32 tensors on `device` (device-to-device copy)"""
+        import torch
+        _, n_p, _, n_m = self.result_dev()
+        counts = torch.empty(max(n_p, 1), dtype=torch.int32, device=device)
+        matches = torch.empty((max(n_m, 1), 2), dtype=torch.int32, device=device)
+        check(self._lib.bsfm_match_copy_result_dev(self._h, counts.data_ptr(), matches.data_ptr()), "bsfm_match_copy_result_dev")
+        return counts[:n_p], matches[:n_m]
+
     def timing(self):
         ms = (ctypes.c_float * 3)()
         launches = ctypes.c_int()

@@ -91,6 +91,9 @@ int bsfm_match_fetch(bsfm_keydb *db, int32_t *pair_counts, int64_t pair_cap,
  * all-gather straight from HBM; *num_pairs / *num_matches receive the element counts          */
 int bsfm_match_result_dev(bsfm_keydb *db, const int32_t **pair_counts_dev, int64_t *num_pairs,
                           const int32_t **matches_dev, int64_t *num_matches);
+/* device-to-device copy of the same two arrays into caller-owned DEVICE buffers (e.g. torch tensors
+ * that then feed torch.distributed all_gather over NCCL)                                        */
+int bsfm_match_copy_result_dev(bsfm_keydb *db, int32_t *pair_counts_dst_dev, int32_t *matches_dst_dev);
 /* number of pairs in the shard of the last run */
 int64_t bsfm_match_shard_pairs(bsfm_keydb *db);
 /* timing of the last bsfm_match_run measured with CUDA events on the launching stream:

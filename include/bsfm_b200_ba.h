@@ -75,6 +75,8 @@ typedef struct {
  *   in/out, cnp in {6,7,8,9}, pnp = 3, x = measurements (2 per visible projection, point-major),
  *   covx must be NULL, mnp = 2, itmax, verbose, opts[6] (reads opts[5], sba_levmar.c:610),
  *   info[10] (sba_levmar.c:2028-2049), camera / point constraints as in sba.h:80-90.
+ * vmask, p and x may be host pointers or device pointers (unified addressing decides the copy kind);
+ * with device pointers no bulk host<->device copy happens inside the call (bench `value` leg).
  * Vout/Sout/Uout/Wout must be NULL (BSFM_ERR_UNSUPPORTED otherwise).
  * Returns the number of iterations (>=0) like the reference, SBA_ERROR (-1) where the reference
  * returns it, or another negative BSFM_ERR_* code.                                              */

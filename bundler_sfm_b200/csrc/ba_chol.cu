@@ -2,16 +2,21 @@
 // Reference: sba_Axb_Chol = LAPACK dpotrf + dpotrs, lib/sba-1.5/sba_lapack.c:374-485.
 //
 // fp64 blocked right-looking Cholesky (lower, row-major) with the right-hand side carried as an
-// extra matrix row (row n), so the forward substitution L y = E falls out of the factorisation;
-// back substitution uses the explicitly inverted 32x32 diagonal blocks.  Two-level blocking: inner
-// panels of 32 columns, outer panels of NBO columns whose trailing update is one large SYRK-shaped
-// GEMM (A22 -= L21 L21^T) -- the dense contraction of this path.
+// extra matrix row (row n), so the forward substitution L y = E falls out of the factorisation.
 //
+// Small systems (n <= 1536, i.e. up to ~170 cameras; latency-bound):
+//   per 32-column step : chol_step_kernel  one launch; every CTA redundantly factors the diagonal
+//                        block fused with the row solves of the two panel blocks its 32x32 trailing
+//                        tile needs, then applies the rank-32 update (critical path: 32 pivots)
+//   end                : chol_backsolve_blocked_kernel (1 CTA) L^T x = y with inverted diagonal blocks
+// Large systems (throughput-bound; the dense contraction of this path):
+//   two-level blocking: inner panels of 32 columns, outer panels of 256 columns whose trailing update is
+//   one large SYRK-shaped GEMM (A22 -= L21 L21^T)
 //   per inner panel k : diag_kernel   (1 CTA)  potf2 of A_kk, L_kk^-1
 //                       trsm_kernel   (rows)   A_rk <- A_rk L_kk^-T   for all rows below (incl. RHS row)
 //                       syrk_kernel   (tiles)  columns inside the outer panel
-//   per outer panel   : syrk_kernel   (tiles)  trailing matrix, K = NBO
-//   end               : backsolve_kernel (1 CTA) L^T x = y
+//   per outer panel   : syrk_kernel   (tiles)  trailing matrix, K = 256
+//   end               : chol_backsolve_kernel (1 CTA) row-oriented L^T x = y
 #include "ba_kernels.cuh"
 #include "common.h"
 
@@ -19,6 +24,13 @@ namespace bsfm {
 namespace ba {
 
 constexpr int NB = 32;
+#ifdef BSFM_DEBUG_CLOCKS
+__device__ long long g_dbg[64];
+__device__ __forceinline__ long long dbg_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
+#define DBG_T(i) do { if (blockIdx.x == 1 && k == 0 && (threadIdx.x & 31) == 0) g_dbg[(i) + 5 * (threadIdx.x >> 5)] = dbg_clock(); } while (0)
+#else
+#define DBG_T(i) do { } while (0)
+#endif
 
 // ---- diagonal block: potf2 + triangular inverse ------------------------------------------------
 __global__ void __launch_bounds__(256) chol_diag_kernel(double *A, int ld, int k0, int nb, double *Linv, Scalars *sc)
@@ -188,37 +200,240 @@ __global__ void __launch_bounds__(1024) chol_panel_smem_kernel(double *A, int ld
     if (tid == 0 && fail) sc->chol_fail = 1;
 }
 
-// ---- back substitution L^T x = y (y = row n of A), single CTA, row-oriented -----------------------
-// thread c owns y_c (columns strided over the CTA); rows are consumed from the last to the first:
+// ---- small systems, one launch per 32-column step ---------------------------------------------------
+// Every CTA redundantly factors the 32x32 diagonal block (one warp, rows in registers, pivots and
+// multipliers exchanged with shuffles), solves the two 32-row panel blocks its tile needs (one warp
+// each, row in registers, L_kk broadcast from shared memory) and applies the rank-32 update to its
+// 32x32 tile of the trailing matrix.  Redundant panel work costs no latency and removes the separate
+// panel / TRSM launches: the critical path per step is potf2 -> trsm -> update inside one kernel.
+// Row block index nbk (= one row) is the right-hand side carried along as matrix row n.
+// (loops over shared memory, not unrolled register code: a kernel that runs ~10 us must not spend it
+// fetching tens of KB of straight-line instructions)
+__global__ void __launch_bounds__(256) chol_step_kernel(double *A, int ld, int n, int k, double *Linv_all, Scalars *sc)
+{
+    __shared__ double Lk[NB][NB + 1];
+    __shared__ double Xr[NB][NB + 1];
+    __shared__ double Xc[NB][NB + 1];
+    __shared__ double Z[NB][NB + 1];
+    __shared__ double dinv[NB];
+    __shared__ int fail_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nbk = (n + NB - 1) / NB;           // matrix row blocks; block nbk = RHS row
+    const int k0 = k * NB, nb = min(NB, n - k0);
+    // tile of this CTA: blockIdx 0 = panel owner (no tile); else (cb, rb), k < cb <= rb <= nbk, cb < nbk
+    int cb = -1, rb = nbk;                        // the owner solves the RHS row segment
+    if (blockIdx.x > 0) {
+        int t = blockIdx.x - 1;
+        for (int c = k + 1; c < nbk; c++) {
+            const int cnt = nbk - c + 1;
+            if (t < cnt) { cb = c; rb = c + t; break; }
+            t -= cnt;
+        }
+    }
+    const int crow0 = cb * NB;
+    const int rrows = (rb == nbk) ? 1 : min(NB, n - rb * NB);        // valid rows in the rb block
+    const int rbase = (rb == nbk) ? n : rb * NB;                      // first matrix row of the rb block
+    const int crows = (cb >= 0) ? min(NB, n - crow0) : 0;
+    const bool need_c = cb >= 0 && cb != rb;
+
+    DBG_T(0);
+    if (tid == 0) fail_s = 0;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        Lk[r][c] = (r < nb && c <= r) ? A[(size_t) (k0 + r) * ld + (k0 + c)] : ((r == c) ? 1.0 : 0.0);
+        Xr[r][c] = (r < rrows && c < nb) ? A[(size_t) (rbase + r) * ld + (k0 + c)] : 0.0;
+        if (need_c) Xc[r][c] = (r < crows && c < nb) ? A[(size_t) (crow0 + r) * ld + (k0 + c)] : 0.0;
+    }
+    __syncthreads();
+    DBG_T(1);
+    // potf2 of L_kk fused with the row solves X <- X L_kk^-T, right-looking, all 8 warps:
+    //   thread (lane r, warp g) owns rows r and columns c = g, g+8, g+16, g+24.
+    //   Every warp recomputes the pivot reciprocal and the multipliers l_r = a_rj / sqrt(d) of column j
+    //   in registers (no communication), updates its own columns of L_kk, Xr and Xc, one barrier per pivot.
+    //   Column j itself is left un-scaled in shared memory (it is read-only from now on) and rescaled by
+    //   dinv[j] after the loop.  The pivot chain is the latency floor of the whole solve: rsqrt + multiply
+    //   instead of sqrt + divide.
+    for (int j = 0; j < nb; j++) {
+        const double d = Lk[j][j];
+        const double arj = Lk[lane][j];
+        const double xr = Xr[lane][j];
+        const double xc = need_c ? Xc[lane][j] : 0.0;
+        const bool bad = !(d > 0.0) || !isfinite(d);
+        const double rinv = bad ? 1.0 : rsqrt(d);
+        const double l = (lane > j) ? arj * rinv : 0.0;
+        const double xjr = xr * rinv, xjc = xc * rinv;
+        if (tid == 0) { dinv[j] = rinv; if (bad) fail_s = 1; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = warp + 8 * q;                      // warp-uniform
+            if (c > j && c < nb) {
+                const double lc = __shfl_sync(0xffffffffu, l, c);   // L[c][j]
+                if (lane >= c) Lk[lane][c] = fma(-l, lc, Lk[lane][c]);
+                Xr[lane][c] = fma(-xjr, lc, Xr[lane][c]);
+                if (need_c) Xc[lane][c] = fma(-xjc, lc, Xc[lane][c]);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < NB && tid >= nb) dinv[tid] = 1.0;
+    __syncthreads();
+    DBG_T(2);
+    // rescale: L[r][c] = a_rc dinv[c] (c < r), L[c][c] = d_c dinv[c], X[r][c] *= dinv[c]
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        const double sc_c = dinv[c];
+        if (c <= r && r < nb) Lk[r][c] *= sc_c;
+        Xr[r][c] *= sc_c;
+        if (need_c) Xc[r][c] *= sc_c;
+    }
+    __syncthreads();
+    if (warp == 3 && blockIdx.x == 0) {
+        // Z = L^-1 (lane c solves L z = e_c) for the blocked back substitution
+        const int c = lane;
+        for (int r = 0; r < NB; r++) {
+            double sacc = (r == c) ? 1.0 : 0.0;
+            for (int t = c; t < r; t++) sacc = fma(-Lk[r][t], Z[t][c], sacc);
+            Z[r][c] = (r < c) ? 0.0 : sacc * dinv[r];
+        }
+    } else if (warp == 4 && blockIdx.x == 0) {
+        for (int c = 0; c < nb; c++) if (lane < nb && c <= lane) A[(size_t) (k0 + lane) * ld + (k0 + c)] = Lk[lane][c];
+        if (lane == 0 && fail_s) sc->chol_fail = 1;
+    }
+    __syncthreads();
+    DBG_T(3);
+    if (blockIdx.x == 0) {
+        for (int e = tid; e < NB * NB; e += 256) Linv_all[(size_t) k * NB * NB + e] = Z[e >> 5][e & 31];
+    }
+    // panel write-back: the owner writes the RHS segment, first-column tiles write their row block
+    if (blockIdx.x == 0 || cb == k + 1) {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e >> 5, c = e & 31;
+            if (r < rrows && c < nb) A[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
+        }
+    }
+    if (cb < 0) return;
+    // trailing tile (rb, cb):  A[r][c] -= sum_t Xr[r][t] Xc[c][t]   (c <= r on the diagonal tile)
+    const double (*XC)[NB + 1] = need_c ? Xc : Xr;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int e = tid + q * 256;
+        const int r = e >> 5, c = e & 31;
+        if (r < rrows && c < crows && (rb != cb || c <= r)) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int t = 0; t < NB; t++) acc = fma(Xr[r][t], XC[c][t], acc);
+            A[(size_t) (rbase + r) * ld + (crow0 + c)] -= acc;
+        }
+    }
+    DBG_T(4);
+}
+
+// ---- back substitution L^T x = y (y = row n of A) with inverted diagonal blocks, single CTA ---------
+// per 32-row block (last to first): x_k = L_kk^-T y_k, then y[0:k0] -= L[k0:k0+nb, 0:k0]^T x_k.
+// Two barriers per block instead of one per row.
+__global__ void __launch_bounds__(512) chol_backsolve_blocked_kernel(const double *A, int ld, int n, const double *Linv_all, double *x)
+{
+    __shared__ double xk[NB];
+    __shared__ double ys[NB];
+    __shared__ double Li[NB][NB + 1];
+    const int tid = threadIdx.x;
+    const double *yrow = A + (size_t) n * ld;
+    constexpr int COLS = 3;                     // n <= 1536
+    double y[COLS];
+#pragma unroll
+    for (int q = 0; q < COLS; q++) { const int c = tid + q * 512; y[q] = (c < n) ? yrow[c] : 0.0; }
+    const int nbk = (n + NB - 1) / NB;
+    for (int kb = nbk - 1; kb >= 0; kb--) {
+        const int k0 = kb * NB, nb = min(NB, n - k0);
+        // everything that does not depend on x_k is issued first: L_kk^-1 block and this thread's
+        // column of the 32 L rows (first 512 columns; the rare wider case is fetched later)
+        const double z0 = Linv_all[(size_t) kb * NB * NB + tid], z1 = Linv_all[(size_t) kb * NB * NB + 512 + tid];
+        double l[NB];
+#pragma unroll
+        for (int r = 0; r < NB; r++) l[r] = (tid < k0 && r < nb) ? A[(size_t) (k0 + r) * ld + tid] : 0.0;
+#pragma unroll
+        for (int q = 0; q < COLS; q++) { const int c = tid + q * 512; if (c >= k0 && c < k0 + nb) ys[c - k0] = y[q]; }
+        Li[tid >> 5][tid & 31] = z0;
+        Li[16 + (tid >> 5)][tid & 31] = z1;
+        __syncthreads();
+        // x_k = L_kk^-T y_k : 8 lanes per output, 4 terms each, shuffle-reduced
+        if (tid < 256) {
+            const int o = tid >> 3, part = tid & 7;
+            double sacc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int r = part * 4 + u; if (r >= o && r < nb) sacc = fma(Li[r][o], ys[r], sacc); }
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+            if (part == 0) { xk[o] = sacc; if (o < nb) x[k0 + o] = sacc; }
+        }
+        __syncthreads();
+        {
+            double sacc = 0.0;
+#pragma unroll
+            for (int r = 0; r < NB; r++) sacc = fma(l[r], xk[r], sacc);
+            y[0] -= sacc;
+        }
+#pragma unroll
+        for (int q = 1; q < COLS; q++) {
+            const int c = tid + q * 512;
+            if (c < k0) {
+                double sacc = 0.0;
+#pragma unroll 8
+                for (int r = 0; r < nb; r++) sacc = fma(A[(size_t) (k0 + r) * ld + c], xk[r], sacc);
+                y[q] -= sacc;
+            }
+        }
+    }
+}
+
+// ---- back substitution L^T x = y (y = row n of A), single CTA, row-oriented (large systems) --------
+// thread c owns y_c; rows are consumed from the last to the first in batches whose L entries are
+// prefetched (double-buffered) so the per-row critical path is one broadcast + one FMA:
 // x_i = y_i / L_ii, then y_c -= L_ic x_i for c < i (row i of L is contiguous => coalesced).
-constexpr int BS_COLS = 9;   // columns per thread: supports n <= 9216 with 1024 threads
+template <int COLS, int BS_BATCH>
 __global__ void __launch_bounds__(1024) chol_backsolve_kernel(const double *A, int ld, int n, double *x)
 {
     __shared__ double xi_s[2];
     const int tid = threadIdx.x;
     const double *yrow = A + (size_t) n * ld;
-    double y[BS_COLS];
+    double y[COLS];
 #pragma unroll
-    for (int q = 0; q < BS_COLS; q++) { const int c = tid + q * 1024; y[q] = (c < n) ? yrow[c] : 0.0; }
-    for (int i = n - 1; i >= 0; i--) {
-        const double *Li = A + (size_t) i * ld;
-        // issue this row's loads before the dependent broadcast
-        double l[BS_COLS];
+    for (int q = 0; q < COLS; q++) { const int c = tid + q * 1024; y[q] = (c < n) ? yrow[c] : 0.0; }
+    double cur[COLS][BS_BATCH], nxt[COLS][BS_BATCH];
+    auto fetch = [&](double (&dst)[COLS][BS_BATCH], int itop) {
 #pragma unroll
-        for (int q = 0; q < BS_COLS; q++) { const int c = tid + q * 1024; l[q] = (c < i) ? Li[c] : 0.0; }
-        const int owner = i & 1023, oq = i >> 10;
-        if (tid == owner) {
-            double yi = 0.0;
+        for (int b = 0; b < BS_BATCH; b++) {
+            const int i = itop - b;
 #pragma unroll
-            for (int q = 0; q < BS_COLS; q++) if (q == oq) yi = y[q];
-            const double xi = yi / Li[i];
-            xi_s[i & 1] = xi;
-            x[i] = xi;
+            for (int q = 0; q < COLS; q++) { const int c = tid + q * 1024; dst[q][b] = (i >= 0 && c <= i) ? A[(size_t) i * ld + c] : 0.0; }
         }
-        __syncthreads();
-        const double xi = xi_s[i & 1];
+    };
+    fetch(cur, n - 1);
+    for (int itop = n - 1; itop >= 0; itop -= BS_BATCH) {
+        fetch(nxt, itop - BS_BATCH);
 #pragma unroll
-        for (int q = 0; q < BS_COLS; q++) y[q] = fma(-l[q], xi, y[q]);
+        for (int b = 0; b < BS_BATCH; b++) {
+            const int i = itop - b;
+            if (i < 0) break;
+            const int owner = i & 1023, oq = i >> 10;
+            if (tid == owner) {
+                double yi = 0.0, lii = 1.0;
+#pragma unroll
+                for (int q = 0; q < COLS; q++) if (q == oq) { yi = y[q]; lii = cur[q][b]; }
+                const double xi = yi / lii;
+                xi_s[i & 1] = xi;
+                x[i] = xi;
+            }
+            __syncthreads();
+            const double xi = xi_s[i & 1];
+#pragma unroll
+            for (int q = 0; q < COLS; q++) { const int c = tid + q * 1024; if (c < i) y[q] = fma(-cur[q][b], xi, y[q]); }
+        }
+#pragma unroll
+        for (int q = 0; q < COLS; q++)
+#pragma unroll
+            for (int b = 0; b < BS_BATCH; b++) cur[q][b] = nxt[q][b];
     }
 }
 
@@ -227,13 +442,27 @@ __global__ void __launch_bounds__(1024) chol_backsolve_kernel(const double *A, i
 int chol_solve(cudaStream_t st, double *A, int n, double *linv_ws, double *x, Scalars *sc)
 {
     const int ld = n, nrows = n + 1;
-    if (n > 1024 * BS_COLS) { set_error("reduced camera system of dimension %d exceeds the supported %d", n, 1024 * BS_COLS); return BSFM_ERR_UNSUPPORTED; }
-    const size_t panel_bytes = (size_t) nrows * PANEL_LD * sizeof(double);
-    const bool small = panel_bytes <= 200 * 1024;
-    if (small) {
-        static bool attr = false;
-        if (!attr) { BSFM_CUDA_TRY(cudaFuncSetAttribute(chol_panel_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (n > 1024 * 9) { set_error("reduced camera system of dimension %d exceeds the supported %d", n, 1024 * 9); return BSFM_ERR_UNSUPPORTED; }
+    auto backsolve = [&]() -> int {
+        if (n <= 4096) chol_backsolve_kernel<4, 2><<<1, 1024, 0, st>>>(A, ld, n, x);
+        else chol_backsolve_kernel<9, 1><<<1, 1024, 0, st>>>(A, ld, n, x);
+        BSFM_KERNEL_CHECK();
+        return BSFM_OK;
+    };
+    if (n <= 1536) {
+        // small reduced systems (<= ~170 cameras): one fused launch per 32-column step
+        const int nbk = (n + NB - 1) / NB;
+        for (int k = 0; k < nbk; k++) {
+            const int R = nbk - 1 - k;                      // remaining column blocks
+            const int tiles = R * (R + 1) / 2 + R;          // (rb, cb) incl. the RHS row block
+            chol_step_kernel<<<1 + tiles, 256, 0, st>>>(A, ld, n, k, linv_ws, sc);
+            BSFM_KERNEL_CHECK();
+        }
+        chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(A, ld, n, linv_ws, x);
+        BSFM_KERNEL_CHECK();
+        return BSFM_OK;
     }
+    const bool small = false;
     const int NBO = (n > 2048) ? 256 : NB;
     const int BT = (n <= 1024) ? 32 : (n <= 4096 ? 64 : 128);
     auto syrk = [&](int cb, int ce, int kb, int ke) -> int {
@@ -278,10 +507,15 @@ int chol_solve(cudaStream_t st, double *A, int n, double *linv_ws, double *x, Sc
             // RHS row (row n) against columns >= K1 is part of the tiles (nrows = n + 1)
         }
     }
-    chol_backsolve_kernel<<<1, 1024, 0, st>>>(A, ld, n, x);
-    BSFM_KERNEL_CHECK();
-    return BSFM_OK;
+    return backsolve();
 }
 
 }  // namespace ba
 }  // namespace bsfm
+
+#ifdef BSFM_DEBUG_CLOCKS
+extern "C" int bsfm_debug_read(long long *out64)
+{
+    return cudaMemcpyFromSymbol(out64, bsfm::ba::g_dbg, sizeof(long long) * 64) == cudaSuccess ? 0 : -2;
+}
+#endif

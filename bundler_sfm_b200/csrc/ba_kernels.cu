@@ -415,15 +415,19 @@ __global__ void v_kernel(Problem P, const double *p, const double *e)
 // fixed-shape tree (warp shuffles + shared memory) combines them: deterministic.
 // ------------------------------------------------------------------------------------------------
 constexpr int U_THREADS = 128;
-__global__ void __launch_bounds__(U_THREADS) u_kernel(Problem P, const double *p, const double *e)
+// pass 1: CTA (j, seg) accumulates the seg-th slice of camera j's observations -> Upart[j][seg][54]
+__global__ void __launch_bounds__(U_THREADS) u_partial_kernel(Problem P, const double *e, int nseg)
 {
-    const int j = blockIdx.x;
+    const int j = blockIdx.x / nseg, seg = blockIdx.x % nseg;
     const int cnp = P.M.cnp;
     double acc[54];   // 45 upper-triangular U entries (row-major) + 9 ea
 #pragma unroll
     for (int q = 0; q < 54; q++) acc[q] = 0.0;
     if (j >= P.mcon) {
-        for (int t = P.cam_ptr[j] + threadIdx.x; t < P.cam_ptr[j + 1]; t += U_THREADS) {
+        const int c0 = P.cam_ptr[j], c1 = P.cam_ptr[j + 1];
+        const int len = (c1 - c0 + nseg - 1) / nseg;
+        const int s0 = c0 + seg * len, s1 = min(c1, s0 + len);
+        for (int t = s0 + threadIdx.x; t < s1; t += U_THREADS) {
             const int o = P.cam_obs[t];
             const double *jA = P.jacA + (size_t) o * 2 * cnp;
             double A0[MAX_CNP], A1[MAX_CNP];
@@ -434,9 +438,9 @@ __global__ void __launch_bounds__(U_THREADS) u_kernel(Problem P, const double *p
 #pragma unroll
             for (int ii = 0; ii < MAX_CNP; ii++)
 #pragma unroll
-                for (int jj = ii; jj < MAX_CNP; jj++) { double s = 0.0; s += A0[ii] * A0[jj]; s += A1[ii] * A1[jj]; acc[q++] += s; }
+                for (int jj = ii; jj < MAX_CNP; jj++) { double sv = 0.0; sv += A0[ii] * A0[jj]; sv += A1[ii] * A1[jj]; acc[q++] += sv; }
 #pragma unroll
-            for (int ii = 0; ii < MAX_CNP; ii++) { double s = 0.0; s += A0[ii] * e0; s += A1[ii] * e1; acc[45 + ii] += s; }
+            for (int ii = 0; ii < MAX_CNP; ii++) { double sv = 0.0; sv += A0[ii] * e0; sv += A1[ii] * e1; acc[45 + ii] += sv; }
         }
     }
     __shared__ double sm[U_THREADS / 32][54];
@@ -450,16 +454,28 @@ __global__ void __launch_bounds__(U_THREADS) u_kernel(Problem P, const double *p
     if (threadIdx.x < 54) {
         double v = sm[0][threadIdx.x];
         for (int w = 1; w < U_THREADS / 32; w++) v += sm[w][threadIdx.x];
-        sm[0][threadIdx.x] = v;
+        P.u_part[((size_t) j * nseg + seg) * 54 + threadIdx.x] = v;
+    }
+}
+
+// pass 2: combine the segments in order, scatter to U_j (full symmetric) and ea_j, add constraints
+__global__ void __launch_bounds__(96) u_final_kernel(Problem P, const double *p, int nseg)
+{
+    __shared__ double sm[54];
+    const int j = blockIdx.x;
+    const int cnp = P.M.cnp;
+    if (threadIdx.x < 54) {
+        double v = 0.0;
+        for (int sgm = 0; sgm < nseg; sgm++) v += P.u_part[((size_t) j * nseg + sgm) * 54 + threadIdx.x];
+        sm[threadIdx.x] = v;
     }
     __syncthreads();
-    // scatter to U_j (full symmetric, cnp x cnp row-major) and ea_j, adding camera constraints
     if (threadIdx.x < 81) {
         const int ii = threadIdx.x / 9, jj = threadIdx.x % 9;
         if (ii < cnp && jj < cnp) {
             const int r = ii < jj ? ii : jj, c = ii < jj ? jj : ii;
             const int q = r * 9 - r * (r - 1) / 2 + (c - r);
-            double v = sm[0][q];
+            double v = sm[q];
             if (ii == jj && P.cam_constrained && j >= P.mcon && P.cam_constrained[(size_t) j * cnp + ii])
                 v += P.cam_weights[(size_t) j * cnp + ii];     // sba_levmar.c:952-963
             P.U[(size_t) j * cnp * cnp + ii * cnp + jj] = v;
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__(U_THREADS) u_kernel(Problem P, const double *p
     } else if (threadIdx.x < 90) {
         const int ii = threadIdx.x - 81;
         if (ii < cnp) {
-            double v = sm[0][45 + ii];
+            double v = sm[45 + ii];
             if (P.cam_constrained && j >= P.mcon && P.cam_constrained[(size_t) j * cnp + ii]) {
                 const double diff = P.cam_constraints[(size_t) j * cnp + ii] - p[(size_t) j * cnp + ii];
                 v += P.cam_weights[(size_t) j * cnp + ii] * diff;
@@ -483,26 +499,24 @@ __global__ void __launch_bounds__(U_THREADS) u_kernel(Problem P, const double *p
 // ------------------------------------------------------------------------------------------------
 __global__ void grad_stats_kernel(Problem P, const double *p)
 {
-    __shared__ double sm[3][32];
     const int cnp = P.M.cnp;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
     double inf = 0.0, pl2 = 0.0, md = DBL_MIN;
-    for (int q = threadIdx.x; q < P.nvars; q += blockDim.x) {
-        inf = fmax(inf, fabs(P.eab[q]));
-        pl2 += p[q] * p[q];
+    if (q < P.nvars) {
+        inf = fabs(P.eab[q]);
+        pl2 = p[q] * p[q];
+        if (q < P.m * cnp) {
+            const int j = q / cnp, ii = q % cnp;
+            if (j >= P.mcon) md = P.U[(size_t) j * cnp * cnp + ii * cnp + ii];
+        } else {
+            const int r = q - P.m * cnp;
+            md = P.V[(size_t) (r / 3) * 9 + (r % 3) * 4];
+        }
     }
-    for (int q = threadIdx.x; q < (P.m - P.mcon) * cnp; q += blockDim.x) {
-        const int j = P.mcon + q / cnp, ii = q % cnp;
-        md = fmax(md, P.U[(size_t) j * cnp * cnp + ii * cnp + ii]);
-    }
-    for (int q = threadIdx.x; q < P.n * 3; q += blockDim.x) md = fmax(md, P.V[(size_t) (q / 3) * 9 + (q % 3) * 4]);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    inf = warp_max(inf); pl2 = warp_sum(pl2); md = warp_max(md);
-    if (lane == 0) { sm[0][wid] = inf; sm[1][wid] = pl2; sm[2][wid] = md; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < nw; w++) { inf = fmax(inf, sm[0][w]); pl2 += sm[1][w]; md = fmax(md, sm[2][w]); }
-        P.sc->eab_inf = inf; P.sc->p_L2 = pl2; P.sc->max_diag = md;
-    }
+    double out;
+    if (grid_reduce<1>(inf, P.partial, P.ticket, out)) P.sc->eab_inf = out;
+    if (grid_reduce<0>(pl2, P.partial + gridDim.x, P.ticket + 1, out)) P.sc->p_L2 = out;
+    if (grid_reduce<1>(md, P.partial + 2 * gridDim.x, P.ticket + 2, out)) P.sc->max_diag = fmax(out, DBL_MIN);
 }
 
 __global__ void penalty_kernel(Problem P, const double *p)
@@ -649,11 +663,19 @@ __global__ void __launch_bounds__(128) schur_final_kernel(Problem P)
     const int j = (int) (key / (uint32_t) m), k = (int) (key % (uint32_t) m);
     const int c0 = P.chunk_off[b], c1 = P.chunk_off[b + 1];
     double acc[3] = {0.0, 0.0, 0.0}, accE = 0.0;
-    for (int c = c0; c < c1; c++) {
-        const double *part = P.schur_part + (size_t) c * SCHUR_PART_STRIDE;
+    for (int c = c0; c < c1; c += 4) {
+        // four chunks' partials are fetched together, then added in chunk order (deterministic)
+        double v[4][4];
 #pragma unroll
-        for (int rep = 0; rep < 3; rep++) { const int q = lane + 32 * rep; if (q < nn) acc[rep] += part[q]; }
-        if (j == k && lane < cnp) accE += part[81 + lane];
+        for (int u = 0; u < 4; u++) {
+            const bool ok = c + u < c1;
+            const double *part = P.schur_part + (size_t) (ok ? c + u : c) * SCHUR_PART_STRIDE;
+#pragma unroll
+            for (int rep = 0; rep < 3; rep++) { const int q = lane + 32 * rep; v[u][rep] = (ok && q < nn) ? part[q] : 0.0; }
+            v[u][3] = (ok && j == k && lane < cnp) ? part[81 + lane] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { acc[0] += v[u][0]; acc[1] += v[u][1]; acc[2] += v[u][2]; accE += v[u][3]; }
     }
     const int Sdim = P.Sdim;
     const int jr = (j - P.mcon) * cnp, kr = (k - P.mcon) * cnp;

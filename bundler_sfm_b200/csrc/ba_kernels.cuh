@@ -14,7 +14,7 @@ namespace ba {
 constexpr int MAX_CNP = 9;
 constexpr int PNP = 3;
 constexpr int MNP = 2;
-constexpr int SCHUR_CHUNK = 32;        // tuples per partial-sum warp
+constexpr int SCHUR_CHUNK = 64;        // tuples per partial-sum warp
 constexpr int SCHUR_PART_STRIDE = 96;  // doubles per partial (81 block entries + 9 E + pad)
 
 struct Model {
@@ -73,6 +73,7 @@ struct Problem {
     double *jacA;     // nvis*2*cnp
     double *jacB;     // nvis*6
     double *W;        // nvis*cnp*3
+    double *u_part;   // m*nseg*54 partial U/ea sums
     double *U;        // m*cnp*cnp (undamped)
     double *V;        // n*9 (undamped, full symmetric)
     double *Vinv;     // n*9 ((V+mu I)^-1, full symmetric)

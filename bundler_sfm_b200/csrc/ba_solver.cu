@@ -23,7 +23,8 @@ __global__ void cam_prep_kernel(Problem, const double *, int);
 __global__ void residual_kernel(Problem, const double *, double *, const double *, double);
 __global__ void jacobian_kernel(Problem, const double *, int);
 __global__ void v_kernel(Problem, const double *, const double *);
-__global__ void u_kernel(Problem, const double *, const double *);
+__global__ void u_partial_kernel(Problem, const double *, int);
+__global__ void u_final_kernel(Problem, const double *, int);
 __global__ void grad_stats_kernel(Problem, const double *);
 __global__ void penalty_kernel(Problem, const double *);
 __global__ void vinv_kernel(Problem);
@@ -352,7 +353,9 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     P.E = P.S + (size_t) Sdim * Sdim;      // RHS lives in matrix row Sdim (see ba_chol.cu)
     TRY(D.alloc(&d_linv, (size_t) ((Sdim + 31) / 32) * 1024)); TRY(D.alloc(&d_da, (size_t) Sdim));
     const int red_blocks_obs = (nvis + 255) / 256, red_blocks_var = (P.nvars + 255) / 256;
-    TRY(D.alloc(&P.partial, (size_t) 2 * std::max(red_blocks_obs, red_blocks_var) + 8));
+    TRY(D.alloc(&P.partial, (size_t) 3 * std::max(red_blocks_obs, red_blocks_var) + 8));
+    const int useg = std::max(1, std::min(32, (nvis / m + 1023) / 1024));   // ~1024 observations per U-accumulation CTA
+    TRY(D.alloc(&P.u_part, (size_t) m * useg * 54));
     TRY(D.alloc(&P.ticket, 4));
     BSFM_CUDA_TRY(cudaMemsetAsync(P.ticket, 0, 4 * sizeof(unsigned int), st));
     TRY(D.alloc(&P.sc, 1));
@@ -407,11 +410,13 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         P.camR = d_camR_a;
         jacobian_kernel<<<(nvis + 127) / 128, 128, 0, st>>>(P, d_p, jac_mode); ++njev;
         BSFM_KERNEL_CHECK();
-        u_kernel<<<m, 128, 0, st>>>(P, d_p, d_e);
+        u_partial_kernel<<<m * useg, 128, 0, st>>>(P, d_e, useg);
+        BSFM_KERNEL_CHECK();
+        u_final_kernel<<<m, 96, 0, st>>>(P, d_p, useg);
         BSFM_KERNEL_CHECK();
         v_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, d_p, d_e);
         BSFM_KERNEL_CHECK();
-        grad_stats_kernel<<<1, 1024, 0, st>>>(P, d_p);
+        grad_stats_kernel<<<red_blocks_var, 256, 0, st>>>(P, d_p);
         BSFM_KERNEL_CHECK();
         PT.end();
         TRY(read_scalars());

@@ -79,3 +79,18 @@ def ba_scene(num_cameras=50, num_points=20000, views_per_point=5, seed=1234, pix
         "pts": pts + pt_noise * rng.standard_normal(pts.shape),
     }
     return scene
+
+
+def write_key_file(path, desc, seed=0):
+    """Lowe text .key file (src/keys2a.cpp:183-253): "<num> 128", then per key "<y> <x> <scale> <ori>" and the
+    128 descriptor values in 7 lines of 20,20,20,20,20,20,8 integers."""
+    rng = np.random.default_rng(seed)
+    n = desc.shape[0]
+    with open(path, "w") as f:
+        f.write(f"{n} 128\n")
+        loc = rng.uniform(0, 1000, size=(n, 2)); sc = rng.uniform(1, 8, size=n); ori = rng.uniform(-3.14, 3.14, size=n)
+        for i in range(n):
+            f.write(f"{loc[i, 0]:.2f} {loc[i, 1]:.2f} {sc[i]:.2f} {ori[i]:.3f}\n")
+            d = desc[i]
+            for a in range(0, 128, 20):
+                f.write(" " + " ".join(str(int(v)) for v in d[a:a + 20]) + "\n")

@@ -11,7 +11,8 @@ class LibraryMissing(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libbsfm_b200.so")
+    # BSFM_LIB_PATH: development override to A/B-test a differently configured build of the same library
+    return os.environ.get("BSFM_LIB_PATH") or os.path.join(_HERE, "libbsfm_b200.so")
 
 
 def load_library():

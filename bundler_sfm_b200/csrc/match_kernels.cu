@@ -241,6 +241,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for the outstanding tcgen05.ld and tie the destination registers to the wait so that no use of them
+// can be scheduled ahead of it (the load writes the registers asynchronously)
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
 
 struct UnitInfo {
     int64_t a_row0;
@@ -350,45 +361,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             }
         }
     } else {
-        // ===================== epilogue (8 warps) =====================
+        // ===================== epilogue (TC_EPI_WARPS warps) =====================
+        constexpr int NPART = TC_EPI_WARPS / 4;            // column parts per 256-column tile
+        constexpr int NCH = TILE_DB / CHUNK / NPART;       // 32-column chunks per warp per tile
         const int quad = warp & 3;               // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;        // which 128 columns of each 256-column tile
+        const int part = (warp - 2) >> 2;        // which 256/NPART columns of each tile
         const int row = quad * 32 + lane;        // query row inside the unit
-        const int etid = threadIdx.x - 64;       // 0..255
+        const int etid = threadIdx.x - 64;       // 0..TC_EPI_THREADS-1
         const int neg2 = P.neg2;                 // runtime -2: keeps the multiply-add on the FMA pipe (IMAD)
-        int *xch = reinterpret_cast<int *>(smem + TC_SMEM_XCH);   // [3][128] exchange between column halves
+        int *xch = reinterpret_cast<int *>(smem + TC_SMEM_XCH);   // [NPART-1][3][128] exchange between column parts
         uint32_t ts = 0, tph = 0;
         for (int u = u_first; u < P.unit_end; u += u_step) {
             const UnitInfo U = decode_unit(P, u);
             const int na = P.norms[U.a_row0 + row];
             int m1 = INT_MAX, s2 = INT_MAX, bchunk = 0;
+            // the norm of the column this thread stages is fetched one tile ahead (hides the L2 latency)
+            int nrm_next = (etid < TILE_DB) ? P.norms[(size_t) U.db_row0 + etid] : 0;
             for (int t = 0; t < U.ntiles_db; t++) {
                 // stage this tile's 256 database norms in shared memory (buffer = accumulator stage)
-                sN[ts * TILE_DB + etid] = P.norms[(size_t) U.db_row0 + (size_t) t * TILE_DB + etid];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (etid < TILE_DB) {
+                    sN[ts * TILE_DB + etid] = nrm_next;
+                    if (t + 1 < U.ntiles_db) nrm_next = P.norms[(size_t) U.db_row0 + (size_t) (t + 1) * TILE_DB + etid];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
                 mbar_wait(bar_t_full + 8 * ts, tph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + ts * TILE_DB + half * (TILE_DB / 2);
-                const int4 *nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB + half * (TILE_DB / 2));
-#pragma unroll 1
-                for (int c = 0; c < TILE_DB / CHUNK / 2; c++) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c * CHUNK, v);
-                    tmem_ld_wait();
+                const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + ts * TILE_DB + part * (TILE_DB / NPART);
+                const int4 *nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB + part * (TILE_DB / NPART));
+                // software pipeline over the TMEM loads: chunk c+1 is in flight while chunk c is reduced
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    uint32_t (&v)[32] = (c & 1) ? vb : va;
+                    uint32_t (&vn)[32] = (c & 1) ? va : vb;
+                    tmem_ld_wait_regs(v);
+                    if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * CHUNK, vn);
                     int cm = INT_MAX;
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         const int4 nb = nb4[c * 8 + q];
-                        // t = |p|^2 - 2 q.p ; three on the FMA pipe (IMAD), one on the ALU pipe (IADD3)
+                        // t = |p|^2 - 2 q.p as IMAD with a runtime multiplier: keeps the arithmetic on the FMA
+                        // pipe and leaves the (slower) ALU pipe to the 3-input minima
                         const int t0 = (int) v[4 * q + 0] * neg2 + nb.x;
                         const int t1 = (int) v[4 * q + 1] * neg2 + nb.y;
                         const int t2 = (int) v[4 * q + 2] * neg2 + nb.z;
-                        const int t3 = nb.w - 2 * (int) v[4 * q + 3];
+                        const int t3 = (int) v[4 * q + 3] * neg2 + nb.w;
                         cm = min(cm, min(min(t0, t1), min(t2, t3)));
                     }
                     // (m1, s2) <- two smallest of {m1, s2, cm}
                     const int hi = max(m1, cm);
-                    if (cm < m1) bchunk = t * (TILE_DB / CHUNK) + half * (TILE_DB / CHUNK / 2) + c;
+                    if (cm < m1) bchunk = t * (TILE_DB / CHUNK) + part * NCH + c;
                     m1 = min(m1, cm);
                     s2 = min(s2, hi);
                 }
@@ -396,17 +419,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                 mbar_arrive(bar_t_empty + 8 * ts);
                 ts ^= 1; if (ts == 0) tph ^= 1;
             }
-            // merge the two column halves of every row (half 1 -> shared memory -> half 0)
-            if (half == 1) { xch[row] = m1; xch[128 + row] = s2; xch[256 + row] = bchunk; }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            // merge the column parts of every row (parts 1.. -> shared memory -> part 0)
+            if (part > 0) { int *x = xch + (part - 1) * 384; x[row] = m1; x[128 + row] = s2; x[256 + row] = bchunk; }
+            asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");
             bool cand = false;
             int d1u = INT_MAX;
-            if (half == 0) {
-                const int o1 = xch[row], o2 = xch[128 + row], ob = xch[256 + row];
-                const int hi = max(m1, o1);
-                if (o1 < m1) bchunk = ob;
-                m1 = min(m1, o1);
-                s2 = min(min(s2, o2), hi);
+            if (part == 0) {
+#pragma unroll
+                for (int pp = 0; pp < NPART - 1; pp++) {
+                    const int *x = xch + pp * 384;
+                    const int o1 = x[row], o2 = x[128 + row], ob = x[256 + row];
+                    const int hi = max(m1, o1);
+                    if (o1 < m1) bchunk = ob;
+                    m1 = min(m1, o1);
+                    s2 = min(min(s2, o2), hi);
+                }
                 // unit finished: provisional ratio test with the upper bound on d1
                 if (na < NORM_PAD_HALF) {
                     const int d0 = na + m1;
@@ -414,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                     cand = (double) d0 < P.ratio_sq * (double) d1u;
                 }
             }
-            asm volatile("bar.sync 3, 256;" ::: "memory");   // xch may be overwritten by the next unit
+            asm volatile("bar.sync 3, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // xch may be overwritten by the next unit
             const unsigned ball = __ballot_sync(0xffffffffu, cand);
             if (ball) {
                 int basepos = 0;

@@ -30,7 +30,10 @@ constexpr int32_t NORM_PAD = 1 << 30;
 constexpr int32_t NORM_PAD_HALF = 1 << 29;
 
 // tensor-core kernel configuration (shared by kernel and launcher)
-constexpr int TC_EPI_WARPS = 8;
+#ifndef BSFM_TC_EPI_WARPS
+#define BSFM_TC_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = BSFM_TC_EPI_WARPS;   // 8 or 16 (2 or 4 warps per TMEM lane quadrant)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr int TC_B_STAGES = 4;
@@ -40,7 +43,7 @@ constexpr int TC_SMEM_A = 0;
 constexpr int TC_SMEM_B = 2 * TC_A_BYTES;
 constexpr int TC_SMEM_N = TC_SMEM_B + TC_B_STAGES * TC_B_BYTES;   // 2 x 256 int32 norms
 constexpr int TC_SMEM_XCH = TC_SMEM_N + 2 * TILE_DB * 4;              // 3 x 128 int32 half-merge exchange
-constexpr int TC_SMEM_BAR = TC_SMEM_XCH + 3 * 128 * 4;
+constexpr int TC_SMEM_BAR = TC_SMEM_XCH + 3 * 3 * 128 * 4;
 constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
 constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 

@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace bsfm {
@@ -40,7 +42,7 @@ __global__ void vmask_fill_kernel(const char *, int, int, const int *, int *, in
 __global__ void tuple_count_kernel(int, int, const int *, const int *, int *);
 __global__ void tuple_fill_kernel(int, int, int, const int *, const int *, const int *, uint32_t *, int2 *);
 __global__ void iota_kernel(int *, int);
-int chol_solve(cudaStream_t, double *, int, double *, double *, Scalars *);
+int chol_solve(cudaStream_t, double *, double *, int, double *, double *, Scalars *);
 
 __global__ void cam_ptr_kernel(const uint32_t *sorted_cam, int nvis, int m, int *cam_ptr)
 {
@@ -70,15 +72,55 @@ static const double SBA_ONE_THIRD = 0.3333333334;         // sba_levmar.c:37
 
 namespace {
 
+// Device blocks are recycled across solves (RunSFM_SBA calls run_sfm once per outlier round on a problem of
+// nearly the same size, src/Bundle.cpp:586-913): cudaMalloc/cudaFree cost ~10-100 us each and a solve of the
+// 50-camera configuration only takes ~20 ms.  Blocks return to a per-process pool when a solve ends.
+struct BlockPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;   // capacity -> pointer
+    size_t pooled_bytes = 0;
+    int device = -1;
+    void bind_device(int dev)   // blocks belong to one device: drop the pool when the caller switches GPUs
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (dev == device) return;
+        for (auto &kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear(); pooled_bytes = 0; device = dev;
+    }
+    void *get(size_t bytes, size_t *cap_out)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
+            void *p = it->second; *cap_out = it->first; pooled_bytes -= it->first;
+            free_blocks.erase(it);
+            return p;
+        }
+        return nullptr;
+    }
+    void put(void *p, size_t cap)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (pooled_bytes + cap > ((size_t) 24 << 30)) { cudaFree(p); return; }   // bound what the pool may hold
+        free_blocks.emplace(cap, p); pooled_bytes += cap;
+    }
+};
+static BlockPool g_pool;
+
 struct DeviceArena {
-    std::vector<void *> ptrs;
-    ~DeviceArena() { for (void *p : ptrs) cudaFree(p); }
+    std::vector<std::pair<void *, size_t>> blocks;
+    ~DeviceArena() { for (auto &b : blocks) g_pool.put(b.first, b.second); }
     template <typename T> int alloc(T **out, size_t count)
     {
-        void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return BSFM_ERR_CUDA; }
-        ptrs.push_back(p);
+        size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t) 255;
+        size_t cap = bytes;
+        void *p = g_pool.get(bytes, &cap);
+        if (!p) {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e)); return BSFM_ERR_CUDA; }
+            cap = bytes;
+        }
+        blocks.push_back({p, cap});
         *out = (T *) p;
         return BSFM_OK;
     }
@@ -138,6 +180,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         if (jm && !strcmp(jm, "analytic")) jac_mode = BSFM_BA_JAC_ANALYTIC;
         if (jm && !strcmp(jm, "fd")) jac_mode = BSFM_BA_JAC_FD;
     }
+    { int dev = 0; BSFM_CUDA_TRY(cudaGetDevice(&dev)); g_pool.bind_device(dev); }
     const long long launches0 = g_kernel_launches.load();
     cudaStream_t st;
     BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -351,7 +394,9 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     TRY(D.alloc(&P.eab, (size_t) P.nvars)); TRY(D.alloc(&P.dp, (size_t) P.nvars));
     TRY(D.alloc(&P.S, ((size_t) Sdim + 1) * Sdim));
     P.E = P.S + (size_t) Sdim * Sdim;      // RHS lives in matrix row Sdim (see ba_chol.cu)
-    TRY(D.alloc(&d_linv, (size_t) ((Sdim + 31) / 32) * 1024)); TRY(D.alloc(&d_da, (size_t) Sdim));
+    double *d_Lmat;
+    TRY(D.alloc(&d_Lmat, ((size_t) Sdim + 1) * Sdim));   // Cholesky factor (out of place)
+    TRY(D.alloc(&d_linv, (size_t) ((Sdim + 31) / 32) * 1024 + (size_t) Sdim + 64)); TRY(D.alloc(&d_da, (size_t) Sdim));
     const int red_blocks_obs = (nvis + 255) / 256, red_blocks_var = (P.nvars + 255) / 256;
     TRY(D.alloc(&P.partial, (size_t) 3 * std::max(red_blocks_obs, red_blocks_var) + 8));
     const int useg = std::max(1, std::min(32, (nvis / m + 1023) / 1024));   // ~1024 observations per U-accumulation CTA
@@ -443,7 +488,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
             BSFM_KERNEL_CHECK();
             PT.end();
             PT.begin(3);
-            TRY(chol_solve(st, P.S, Sdim, d_linv, d_da, P.sc));
+            TRY(chol_solve(st, P.S, d_Lmat, Sdim, d_linv, d_da, P.sc));
             PT.end();
             PT.begin(4);
             backsub_kernel<<<(std::max(n, m * cnp) + 127) / 128, 128, 0, st>>>(P, d_da);

@@ -370,24 +370,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
         const int etid = threadIdx.x - 64;       // 0..TC_EPI_THREADS-1
         const int neg2 = P.neg2;                 // runtime -2: keeps the multiply-add on the FMA pipe (IMAD)
         int *xch = reinterpret_cast<int *>(smem + TC_SMEM_XCH);   // [NPART-1][3][128] exchange between column parts
+        int *sNall = reinterpret_cast<int *>(smem + TC_SMEM_NALL);
+        int staged_row0 = -1;
         uint32_t ts = 0, tph = 0;
         for (int u = u_first; u < P.unit_end; u += u_step) {
             const UnitInfo U = decode_unit(P, u);
             const int na = P.norms[U.a_row0 + row];
             int m1 = INT_MAX, s2 = INT_MAX, bchunk = 0;
-            // the norm of the column this thread stages is fetched one tile ahead (hides the L2 latency)
-            int nrm_next = (etid < TILE_DB) ? P.norms[(size_t) U.db_row0 + etid] : 0;
-            for (int t = 0; t < U.ntiles_db; t++) {
-                // stage this tile's 256 database norms in shared memory (buffer = accumulator stage)
-                if (etid < TILE_DB) {
-                    sN[ts * TILE_DB + etid] = nrm_next;
-                    if (t + 1 < U.ntiles_db) nrm_next = P.norms[(size_t) U.db_row0 + (size_t) (t + 1) * TILE_DB + etid];
-                }
+            // Database norms: when the whole image fits (<= TC_NORM_CAP rows) they are staged ONCE per
+            // (CTA, database image) -- consecutive units of a CTA share the image -- so the tile loop has
+            // no CTA-level barrier; larger images fall back to staging 256 norms per tile.
+            const bool whole = U.ntiles_db * TILE_DB <= TC_NORM_CAP;
+            if (whole && staged_row0 != U.db_row0) {
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // everyone done with the old image
+                for (int q = etid; q < U.ntiles_db * TILE_DB; q += TC_EPI_THREADS) sNall[q] = P.norms[(size_t) U.db_row0 + q];
                 asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+                staged_row0 = U.db_row0;
+            }
+            int nrm_next = (!whole && etid < TILE_DB) ? P.norms[(size_t) U.db_row0 + etid] : 0;
+            for (int t = 0; t < U.ntiles_db; t++) {
+                const int4 *nb4;
+                if (whole) {
+                    nb4 = reinterpret_cast<const int4 *>(sNall + t * TILE_DB + part * (TILE_DB / NPART));
+                } else {
+                    // stage this tile's 256 database norms in shared memory (buffer = accumulator stage)
+                    if (etid < TILE_DB) {
+                        sN[ts * TILE_DB + etid] = nrm_next;
+                        if (t + 1 < U.ntiles_db) nrm_next = P.norms[(size_t) U.db_row0 + (size_t) (t + 1) * TILE_DB + etid];
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+                    nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB + part * (TILE_DB / NPART));
+                }
                 mbar_wait(bar_t_full + 8 * ts, tph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + ts * TILE_DB + part * (TILE_DB / NPART);
-                const int4 *nb4 = reinterpret_cast<const int4 *>(sN + ts * TILE_DB + part * (TILE_DB / NPART));
                 // software pipeline over the TMEM loads: chunk c+1 is in flight while chunk c is reduced
                 uint32_t va[32], vb[32];
                 tmem_ld32(taddr, va);

@@ -43,7 +43,9 @@ constexpr int TC_SMEM_A = 0;
 constexpr int TC_SMEM_B = 2 * TC_A_BYTES;
 constexpr int TC_SMEM_N = TC_SMEM_B + TC_B_STAGES * TC_B_BYTES;   // 2 x 256 int32 norms
 constexpr int TC_SMEM_XCH = TC_SMEM_N + 2 * TILE_DB * 4;              // 3 x 128 int32 half-merge exchange
-constexpr int TC_SMEM_BAR = TC_SMEM_XCH + 3 * 3 * 128 * 4;
+constexpr int TC_NORM_CAP = 8192;                                      // norms of a whole database image kept in smem
+constexpr int TC_SMEM_NALL = TC_SMEM_XCH + 3 * 3 * 128 * 4;
+constexpr int TC_SMEM_BAR = TC_SMEM_NALL + TC_NORM_CAP * 4;
 constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
 constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 

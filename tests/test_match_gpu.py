@@ -37,7 +37,7 @@ def test_golden_edge_cases(kernel):
             assert np.array_equal(got, gold[f"edge_{name}_{tag}"]), (kernel, name, tag)
 
 
-@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 2), (5, 3), (128, 256), (129, 257), (1000, 777), (2500, 5000)])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 2), (5, 3), (128, 256), (129, 257), (1000, 777), (2500, 5000), (300, 9000)])
 def test_pair_vs_oracle_sizes(kernel, oracle, n1, n2):
     imgs = synth.sift_like_descriptors(2, [n1, n2], seed=n1 * 7 + n2)
     got = keymatch.match_keys(imgs[0], imgs[1], 0.6)

@@ -189,6 +189,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// same, for the single-thread producer / MMA-issuer roles: back off between polls so that the spinning
+// thread does not take issue slots from the epilogue warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -321,13 +337,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             uint32_t bs = 0, bph = 0, as = 0, aph = 0;
             for (int u = u_first; u < P.unit_end; u += u_step) {
                 const UnitInfo U = decode_unit(P, u);
-                mbar_wait(bar_a_empty + 8 * as, aph ^ 1);
+                mbar_wait_backoff(bar_a_empty + 8 * as, aph ^ 1);
                 mbar_expect_tx(bar_a_full + 8 * as, TC_A_BYTES);
                 tma_bulk_g2s(sA + as * TC_A_BYTES, P.keys_sw + (size_t) U.a_row0 * DESC_BYTES, TC_A_BYTES, bar_a_full + 8 * as);
                 as ^= 1; if (as == 0) aph ^= 1;
                 const uint8_t *src = P.keys_sw + (size_t) U.db_row0 * DESC_BYTES;
                 for (int t = 0; t < U.ntiles_db; t++) {
-                    mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+                    mbar_wait_backoff(bar_b_empty + 8 * bs, bph ^ 1);
                     mbar_expect_tx(bar_b_full + 8 * bs, TC_B_BYTES);
                     tma_bulk_g2s(sB + bs * TC_B_BYTES, src + (size_t) t * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * bs);
                     if (++bs == TC_B_STAGES) { bs = 0; bph ^= 1; }
@@ -340,11 +356,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             uint32_t bs = 0, bph = 0, as = 0, aph = 0, ts = 0, tph = 0;
             for (int u = u_first; u < P.unit_end; u += u_step) {
                 const UnitInfo U = decode_unit(P, u);
-                mbar_wait(bar_a_full + 8 * as, aph);
+                mbar_wait_backoff(bar_a_full + 8 * as, aph);
                 const uint64_t adesc = make_sw128_desc(sA + as * TC_A_BYTES);
                 for (int t = 0; t < U.ntiles_db; t++) {
-                    mbar_wait(bar_b_full + 8 * bs, bph);
-                    mbar_wait(bar_t_empty + 8 * ts, tph ^ 1);
+                    mbar_wait_backoff(bar_b_full + 8 * bs, bph);
+                    mbar_wait_backoff(bar_t_empty + 8 * ts, tph ^ 1);
                     tc_fence_after();
                     const uint64_t bdesc = make_sw128_desc(sB + bs * TC_B_BYTES);
                     const uint32_t tmem_d = tmem_base + ts * TILE_DB;
@@ -423,7 +439,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                         const int t1 = (int) v[4 * q + 1] * neg2 + nb.y;
                         const int t2 = (int) v[4 * q + 2] * neg2 + nb.z;
                         const int t3 = (int) v[4 * q + 3] * neg2 + nb.w;
-                        cm = min(cm, min(min(t0, t1), min(t2, t3)));
+                        // two 3-input minima per four elements (VIMNMX3)
+                        const int x3 = min(min(t0, t1), t2);
+                        cm = min(min(x3, t3), cm);
                     }
                     // (m1, s2) <- two smallest of {m1, s2, cm}
                     const int hi = max(m1, cm);

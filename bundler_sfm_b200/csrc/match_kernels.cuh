@@ -31,9 +31,9 @@ constexpr int32_t NORM_PAD_HALF = 1 << 29;
 
 // tensor-core kernel configuration (shared by kernel and launcher)
 #ifndef BSFM_TC_EPI_WARPS
-#define BSFM_TC_EPI_WARPS 8
+#define BSFM_TC_EPI_WARPS 16
 #endif
-constexpr int TC_EPI_WARPS = BSFM_TC_EPI_WARPS;   // 8 or 16 (2 or 4 warps per TMEM lane quadrant)
+constexpr int TC_EPI_WARPS = BSFM_TC_EPI_WARPS;   // 8 or 16 (2 or 4 warps per TMEM lane quadrant); 16 measured best once norms are staged per image
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr int TC_B_STAGES = 4;

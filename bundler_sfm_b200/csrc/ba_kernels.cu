@@ -840,6 +840,38 @@ __global__ void chunk_count_kernel(const int *blk_cnt, int nblocks, int *chunk_c
     else if (b == nblocks) chunk_cnt[b] = 0;
 }
 
+// Wout export (sba_levmar.c:1835-1846): dense (m*cnp) x (3n) matrix, W_ij at rows j*cnp.., columns 3i..
+__global__ void wout_scatter_kernel(Problem P, double *Wout)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= P.nvis) return;
+    const int cnp = P.M.cnp, j = P.obs_cam[o], i = P.obs_pt[o];
+    if (j < P.mcon) return;
+    const double *Wo = P.W + (size_t) o * cnp * 3;
+    for (int ii = 0; ii < cnp; ii++)
+        for (int jj = 0; jj < 3; jj++) Wout[((size_t) j * cnp + ii) * 3 * (size_t) P.n + (size_t) i * 3 + jj] = Wo[ii * 3 + jj];
+}
+
+// undamped (V_i)^-1 for the export pass; a singular V_i becomes 100 I (the reference's recovery, sba_levmar.c:1774-1783)
+__global__ void vinv_export_kernel(Problem P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const double *V = P.V + (size_t) i * 9;
+    const double a00 = V[0], a01 = V[1], a02 = V[2], a11 = V[4], a12 = V[5], a22 = V[8];
+    const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    double *O = P.Vinv + (size_t) i * 9;
+    if (!(det != 0.0) || !isfinite(det)) {
+        for (int q = 0; q < 9; q++) O[q] = (q % 4 == 0) ? 100.0 : 0.0;
+        return;
+    }
+    const double id = 1.0 / det;
+    O[0] = c00 * id; O[1] = c01 * id; O[2] = c02 * id;
+    O[3] = c01 * id; O[4] = (a00 * a22 - a02 * a02) * id; O[5] = (a01 * a02 - a00 * a12) * id;
+    O[6] = c02 * id; O[7] = O[5]; O[8] = (a00 * a11 - a01 * a01) * id;
+}
+
 __global__ void iota_kernel(int *v, int count)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;

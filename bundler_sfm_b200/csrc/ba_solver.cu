@@ -42,6 +42,8 @@ __global__ void vmask_fill_kernel(const char *, int, int, const int *, int *, in
 __global__ void tuple_count_kernel(int, int, const int *, const int *, int *);
 __global__ void tuple_fill_kernel(int, int, int, const int *, const int *, const int *, uint32_t *, int2 *);
 __global__ void iota_kernel(int *, int);
+__global__ void wout_scatter_kernel(Problem, double *);
+__global__ void vinv_export_kernel(Problem);
 int chol_solve(cudaStream_t, double *, double *, int, double *, double *, Scalars *);
 
 __global__ void cam_ptr_kernel(const uint32_t *sorted_cam, int nvis, int m, int *cam_ptr)
@@ -173,7 +175,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         return BSFM_ERR_UNSUPPORTED;
     }
     if (covx) { set_error("bsfm_sba_motstr_levmar_model: covx != NULL is not supported (Bundler always passes NULL, sfm.c:821)"); return BSFM_ERR_UNSUPPORTED; }
-    if (Vout || Sout || Uout || Wout) { set_error("bsfm_sba_motstr_levmar_model: Vout/Sout/Uout/Wout export is not supported yet"); return BSFM_ERR_UNSUPPORTED; }
+    if ((Sout || Uout || Wout) && mcon != 0) { set_error("bsfm_sba_motstr_levmar_model: Sout/Uout/Wout export assumes mcon == 0 (as the reference does, sba_levmar.c:2017-2022)"); return BSFM_ERR_UNSUPPORTED; }
     if ((int64_t) m * m > 0xffffffffLL) { set_error("too many cameras"); return BSFM_ERR_ARG; }
     {
         const char *jm = getenv("BSFM_BA_JAC");
@@ -461,6 +463,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         BSFM_KERNEL_CHECK();
         v_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, d_p, d_e);
         BSFM_KERNEL_CHECK();
+        if (Vout) BSFM_CUDA_TRY(cudaMemcpyAsync(Vout, P.V, (size_t) n * 9 * sizeof(double), cudaMemcpyDefault, st));   // :1039-1051
         grad_stats_kernel<<<red_blocks_var, 256, 0, st>>>(P, d_p);
         BSFM_KERNEL_CHECK();
         PT.end();
@@ -558,6 +561,39 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     }
     if (itno >= itmax) stop = 3;
 
+    if (Sout) {
+        // export pass (sba_levmar.c:1633-2026): Jacobian at the final p, U/V/W with constraints, UNDAMPED Schur complement
+        P.camR = d_camR_a;
+        jacobian_kernel<<<(nvis + 127) / 128, 128, 0, st>>>(P, d_p, jac_mode); ++njev;
+        BSFM_KERNEL_CHECK();
+        u_partial_kernel<<<m * useg, 128, 0, st>>>(P, d_e, useg);
+        BSFM_KERNEL_CHECK();
+        u_final_kernel<<<m, 96, 0, st>>>(P, d_p, useg);
+        BSFM_KERNEL_CHECK();
+        v_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, d_p, d_e);
+        BSFM_KERNEL_CHECK();
+        if (Uout) BSFM_CUDA_TRY(cudaMemcpyAsync(Uout, P.U, (size_t) m * cnp * cnp * sizeof(double), cudaMemcpyDefault, st));
+        if (Vout) BSFM_CUDA_TRY(cudaMemcpyAsync(Vout, P.V, (size_t) n * 9 * sizeof(double), cudaMemcpyDefault, st));
+        vinv_export_kernel<<<(n + 255) / 256, 256, 0, st>>>(P);
+        BSFM_KERNEL_CHECK();
+        if (Wout) {
+            double *d_wout;
+            TRY(D.alloc(&d_wout, (size_t) m * cnp * 3 * (size_t) n));
+            BSFM_CUDA_TRY(cudaMemcpyAsync(d_wout, Wout, (size_t) m * cnp * 3 * (size_t) n * sizeof(double), cudaMemcpyDefault, st));   // untouched entries keep the caller's values
+            wout_scatter_kernel<<<(nvis + 255) / 256, 256, 0, st>>>(P, d_wout);
+            BSFM_KERNEL_CHECK();
+            BSFM_CUDA_TRY(cudaMemcpyAsync(Wout, d_wout, (size_t) m * cnp * 3 * (size_t) n * sizeof(double), cudaMemcpyDefault, st));
+        }
+        *h_mu = 0.0;
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_mu, h_mu, sizeof(double), cudaMemcpyHostToDevice, st));
+        zero_kernel<<<std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, 0, st>>>(P.S, (size_t) Sdim * Sdim);
+        BSFM_KERNEL_CHECK();
+        schur_partial_kernel<<<(nchunks * 32 + 127) / 128, 128, 0, st>>>(P);
+        BSFM_KERNEL_CHECK();
+        schur_final_kernel<<<(nblocks * 32 + 127) / 128, 128, 0, st>>>(P);
+        BSFM_KERNEL_CHECK();
+        BSFM_CUDA_TRY(cudaMemcpyAsync(Sout, P.S, (size_t) Sdim * Sdim * sizeof(double), cudaMemcpyDefault, st));   // symmetric: transpose == itself (:2017-2025)
+    }
     BSFM_CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));
     BSFM_CUDA_TRY(cudaEventRecord(ev_end, st));
     BSFM_CUDA_TRY(cudaStreamSynchronize(st));

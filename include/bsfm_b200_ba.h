@@ -77,7 +77,8 @@ typedef struct {
  *   info[10] (sba_levmar.c:2028-2049), camera / point constraints as in sba.h:80-90.
  * vmask, p and x may be host pointers or device pointers (unified addressing decides the copy kind);
  * with device pointers no bulk host<->device copy happens inside the call (bench `value` leg).
- * Vout/Sout/Uout/Wout must be NULL (BSFM_ERR_UNSUPPORTED otherwise).
+ * Vout/Sout/Uout/Wout (nullable) export the undamped V (n x 9), reduced camera matrix S ((m cnp)^2), U (m x cnp^2)
+ * and W (dense (m cnp) x (3n)) like sba_levmar.c:1633-2026 (extra Jacobian + Schur pass when Sout != NULL; mcon == 0).
  * Returns the number of iterations (>=0) like the reference, SBA_ERROR (-1) where the reference
  * returns it, or another negative BSFM_ERR_* code.                                              */
 int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,

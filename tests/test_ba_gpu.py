@@ -174,3 +174,20 @@ def test_multiwave_system_vs_oracle(oracle):
     got = bundle.run_sfm(scene)
     ref = oracle.run_sfm_oracle(scene)
     check_solution(got, ref, scene["projections"].shape[0], "multiwave500")
+
+
+def test_export_of_U_V_W_S_vs_reference(oracle):
+    """Vout/Sout/Uout/Wout (sba_levmar.c:1633-2026; Bundler asks for S in its first two-camera solve,
+    src/Bundle.cpp:2150-2154): undamped blocks at the returned solution"""
+    if oracle.ref_sba() is None:
+        pytest.skip("needs oracle/_ref (the C restatement does not export the blocks)")
+    for m, n, L, keys in ((3, 80, 3, "S"), (6, 120, 3, "SUVW")):
+        scene = synth.ba_scene(m, n, L, seed=40 + m)
+        got = bundle.run_sfm(scene, export=keys)
+        ref = oracle.run_sfm_ref(scene, export=keys)
+        check_solution(got, ref, scene["projections"].shape[0], f"export{m}")
+        for key in keys:
+            scale = np.max(np.abs(ref[key]))
+            # same gate as the parameters: the blocks are evaluated at solutions that agree to ~1e-7 and S = U - Y W^T cancels
+            assert np.max(np.abs(got[key] - ref[key])) <= PARAM_TOL * scale, (m, key, np.max(np.abs(got[key] - ref[key])) / scale)
+        assert np.allclose(got["S"], got["S"].T)

@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
     __shared__ double Lk[NB][NB + 1];
     __shared__ double Xr[NB][NB + 1];
     __shared__ double Xc[NB][NB + 1];
-    __shared__ double Z[NB][NB + 1];
     __shared__ double dinv[NB];
     __shared__ int fail_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -222,7 +221,10 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
     const int rrows = (rb == nbk) ? 1 : min(NB, n - rb * NB);        // valid rows in the rb block
     const int rbase = (rb == nbk) ? n : rb * NB;                      // first matrix row of the rb block
     const int crows = (cb >= 0) ? min(NB, n - crow0) : 0;
-    const bool need_c = cb >= 0 && cb != rb;
+    // the owner CTA runs the identity through the second row-solve slot: I L_kk^-T = (L_kk^-1)^T comes out of the
+    // fused loop for free (needed by the blocked back substitution and by chol_tile_kernel)
+    const bool owner = blockIdx.x == 0;
+    const bool need_c = owner || (cb >= 0 && cb != rb);
 
     DBG_T(0);
     if (tid == 0) fail_s = 0;
@@ -230,7 +232,8 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
         const int r = e >> 5, c = e & 31;
         Lk[r][c] = (r < nb && c <= r) ? A[(size_t) (k0 + r) * ld + (k0 + c)] : ((r == c) ? 1.0 : 0.0);
         Xr[r][c] = (r < rrows && c < nb) ? A[(size_t) (rbase + r) * ld + (k0 + c)] : 0.0;
-        if (need_c) Xc[r][c] = (r < crows && c < nb) ? A[(size_t) (crow0 + r) * ld + (k0 + c)] : 0.0;
+        if (owner) Xc[r][c] = (r == c) ? 1.0 : 0.0;
+        else if (need_c) Xc[r][c] = (r < crows && c < nb) ? A[(size_t) (crow0 + r) * ld + (k0 + c)] : 0.0;
     }
     __syncthreads();
     DBG_T(1);
@@ -275,22 +278,14 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
         if (need_c) Xc[r][c] *= sc_c;
     }
     __syncthreads();
-    if (warp == 3 && blockIdx.x == 0) {
-        // Z = L^-1 (lane c solves L z = e_c) for the blocked back substitution
-        const int c = lane;
-        for (int r = 0; r < NB; r++) {
-            double sacc = (r == c) ? 1.0 : 0.0;
-            for (int t = c; t < r; t++) sacc = fma(-Lk[r][t], Z[t][c], sacc);
-            Z[r][c] = (r < c) ? 0.0 : sacc * dinv[r];
-        }
-    } else if (warp == 4 && blockIdx.x == 0) {
+    if (warp == 4 && owner) {
         for (int c = 0; c < nb; c++) if (lane < nb && c <= lane) Lout[(size_t) (k0 + lane) * ld + (k0 + c)] = Lk[lane][c];
         if (lane == 0 && fail_s) sc->chol_fail = 1;
     }
     __syncthreads();
     DBG_T(3);
-    if (blockIdx.x == 0) {
-        for (int e = tid; e < NB * NB; e += 256) Linv_all[(size_t) k * NB * NB + e] = Z[e >> 5][e & 31];
+    if (owner) {   // Z = L_kk^-1 = Xc^T (lower triangular)
+        for (int e = tid; e < NB * NB; e += 256) { const int r = e >> 5, c = e & 31; Linv_all[(size_t) k * NB * NB + e] = (c <= r) ? Xc[c][r] : 0.0; }
     }
     // panel write-back goes to the SEPARATE factor matrix Lout: other CTAs of this launch (possibly in a later
     // wave) still read the un-solved panel blocks from A, so A's panel columns must not change during the step.
@@ -316,6 +311,82 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
         }
     }
     DBG_T(4);
+}
+
+// ---- large grids: tile kernel that takes L_kk^-1 from a preceding diagonal-only chol_step launch -------
+// When a step has far more tiles than the GPU holds at once, redoing the 32-pivot chain in every CTA costs
+// throughput instead of hiding latency.  The step is then split: chol_step_kernel<<<1>>> factors the diagonal
+// block (and solves the RHS segment), and this kernel forms the panel blocks with one small GEMM
+// X = B Z^T (Z = L_kk^-1, lower triangular) before the rank-32 tile update.  Same tile enumeration and the
+// same out-of-place write-back rules as chol_step_kernel (without its CTA 0).
+__global__ void __launch_bounds__(256) chol_tile_kernel(double *A, double *Lout, int ld, int n, int k, int cend, const double *Linv_all)
+{
+    __shared__ double Zs[NB][NB + 1];
+    __shared__ double Br[NB][NB + 1];
+    __shared__ double Bc[NB][NB + 1];
+    __shared__ double Xr[NB][NB + 1];
+    __shared__ double Xc[NB][NB + 1];
+    const int tid = threadIdx.x;
+    const int nbk = (n + NB - 1) / NB;
+    const int k0 = k * NB, nb = min(NB, n - k0);
+    int cb = -1, rb = nbk;
+    bool writeback = true;
+    {
+        int t = blockIdx.x;
+        bool found = false;
+        for (int c = k + 1; c < cend; c++) {
+            const int cnt = nbk - c + 1;
+            if (t < cnt) { cb = c; rb = c + t; found = true; break; }
+            t -= cnt;
+        }
+        if (found) writeback = (cb == k + 1); else rb = k + 1 + t;
+    }
+    const int crow0 = cb * NB;
+    const int rrows = (rb == nbk) ? 1 : min(NB, n - rb * NB);
+    const int rbase = (rb == nbk) ? n : rb * NB;
+    const int crows = (cb >= 0) ? min(NB, n - crow0) : 0;
+    const bool need_c = cb >= 0 && cb != rb;
+    const double *Z = Linv_all + (size_t) k * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        Zs[r][c] = Z[e];
+        Br[r][c] = (r < rrows && c < nb) ? A[(size_t) (rbase + r) * ld + (k0 + c)] : 0.0;
+        if (need_c) Bc[r][c] = (r < crows && c < nb) ? A[(size_t) (crow0 + r) * ld + (k0 + c)] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int e = tid + q * 256;
+        const int r = e >> 5, c = e & 31;
+        double xr = 0.0, xc = 0.0;
+        for (int t = 0; t <= c; t++) {
+            const double z = Zs[c][t];
+            xr = fma(Br[r][t], z, xr);
+            if (need_c) xc = fma(Bc[r][t], z, xc);
+        }
+        Xr[r][c] = xr;
+        if (need_c) Xc[r][c] = xc;
+    }
+    __syncthreads();
+    if (writeback) {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e >> 5, c = e & 31;
+            if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
+        }
+    }
+    if (cb < 0) return;
+    const double (*XC)[NB + 1] = need_c ? Xc : Xr;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int e = tid + q * 256;
+        const int r = e >> 5, c = e & 31;
+        if (r < rrows && c < crows && (rb != cb || c <= r)) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int t = 0; t < NB; t++) acc = fma(Xr[r][t], XC[c][t], acc);
+            A[(size_t) (rbase + r) * ld + (crow0 + c)] -= acc;
+        }
+    }
 }
 
 // ---- back substitution L^T x = y (y = row n of A) with inverted diagonal blocks, single CTA ---------
@@ -395,8 +466,16 @@ int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws,
             int tiles = 0;
             for (int c = k + 1; c < cend; c++) tiles += nbk - c + 1;
             const int extra = (k + 1 >= cend) ? (nbk - 1 - k) : 0;
-            chol_step_kernel<<<1 + tiles + extra, 256, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws, sc);
-            BSFM_KERNEL_CHECK();
+            if (tiles + extra > 800) {
+                // many more tiles than resident CTAs: factor the diagonal block once, then the GEMM-style tile kernel
+                chol_step_kernel<<<1, 256, 0, st>>>(A, Lmat, ld, n, k, k + 1, linv_ws, sc);
+                BSFM_KERNEL_CHECK();
+                chol_tile_kernel<<<tiles + extra, 256, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws);
+                BSFM_KERNEL_CHECK();
+            } else {
+                chol_step_kernel<<<1 + tiles + extra, 256, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws, sc);
+                BSFM_KERNEL_CHECK();
+            }
         }
         if (K1 < n) {
             const int BT = 128;

@@ -37,49 +37,67 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (recipe in B200_PROFILING.md)"""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML in-process (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; an external `nvidia-smi -lms 100` loop was
+    measured to slow the host-side CUDA calls of the timed loop by ~4x, so it is not used)."""
 
-    def __init__(self, gpu_index):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index, period_s=0.05):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.period = period_s
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # map the CUDA device to its NVML handle through the PCI bus id (CUDA_VISIBLE_DEVICES safe)
+            import torch
+            bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.gpu), "pci_bus_id") else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu) if bus is None else None
+            if self.handle is None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+                        break
+                if self.handle is None:
+                    self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:   # NVML missing: report it, never fake a clock
+            self.nvml = None
+            self.err = str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = [s[0] for s in self.samples]
+        reasons = set()
+        for _, _, rs in self.samples:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(s[1] for s in self.samples)) if sm else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -111,8 +129,8 @@ def run_reference_ba(steps, warmup, procs):
     """`procs` independent reference processes (the reference is single-threaded and not re-entrant,
     SURVEY.md F6), each solving the config-2 scene `steps` times: aggregate LM iterations / s."""
     import multiprocessing as mp
-    from oracle import loader
-    kind = "reference" if loader.ref_sba() is not None else "port"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"    # before anything loads OpenBLAS: one BLAS thread per process
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_sba.so")) else "port"
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
         if warmup > 0:
@@ -141,8 +159,7 @@ def _ref_match_worker(args):
 
 def run_reference_match(pairs_per_proc, procs):
     import multiprocessing as mp
-    from oracle import loader
-    kind = "reference" if loader.ref_match() is not None else "port"
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_match.so")) else "port"
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
         pool.map(_ref_match_worker, [(7 + r, 1) for r in range(procs)])
@@ -171,7 +188,7 @@ def main_reference(args):
                 "e2e": {"value": dps, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "image_pairs_per_s": ips}
     else:
-        steps = max(1, min(args.steps, 6))
+        steps = max(1, min(args.steps, 3))
         ips, wall, kind, its = run_reference_ba(steps, min(args.warmup, 1), procs)
         line = {"impl": "reference", "metric": "LM iterations/s (sparse bundle adjustment solve)", "value": ips, "unit": "LM iterations/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
@@ -334,9 +351,9 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
 
 
 def cpu_baseline_ba():
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from bundler_sfm_b200 import synth
     from oracle import loader
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
     scene = synth.ba_scene(seed=1234, **BA_CFG)
     t0 = time.perf_counter()
     out = loader.run_sfm_oracle(scene)

@@ -184,15 +184,28 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     }
     { int dev = 0; BSFM_CUDA_TRY(cudaGetDevice(&dev)); g_pool.bind_device(dev); }
     const long long launches0 = g_kernel_launches.load();
-    cudaStream_t st;
-    BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sguard{st};
+    // stream, events and the pinned scalar blocks are created once per thread and device and reused: driver
+    // calls that allocate (cudaMallocHost, cudaStreamCreate, ...) serialise on a global lock and cost more than
+    // an LM iteration of the 50-camera configuration
+    struct SolverCtx { int device = -1; cudaStream_t st = nullptr; cudaEvent_t ev_begin = nullptr, ev_end = nullptr; Scalars *h_sc = nullptr; double *h_mu = nullptr; };
+    static thread_local SolverCtx ctx;
+    {
+        int dev = 0;
+        BSFM_CUDA_TRY(cudaGetDevice(&dev));
+        if (ctx.device != dev) {
+            if (ctx.st) { cudaStreamDestroy(ctx.st); cudaEventDestroy(ctx.ev_begin); cudaEventDestroy(ctx.ev_end); cudaFreeHost(ctx.h_sc); cudaFreeHost(ctx.h_mu); ctx = SolverCtx(); }
+            BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx.st, cudaStreamNonBlocking));
+            BSFM_CUDA_TRY(cudaEventCreate(&ctx.ev_begin));
+            BSFM_CUDA_TRY(cudaEventCreate(&ctx.ev_end));
+            BSFM_CUDA_TRY(cudaMallocHost(&ctx.h_sc, sizeof(Scalars)));
+            BSFM_CUDA_TRY(cudaMallocHost(&ctx.h_mu, sizeof(double)));
+            ctx.device = dev;
+        }
+    }
+    cudaStream_t st = ctx.st;
     const bool timing_on = getenv("BSFM_BA_TIMING") != nullptr;
     PhaseTimer PT(st, timing_on);
-    cudaEvent_t ev_begin, ev_end;
-    BSFM_CUDA_TRY(cudaEventCreate(&ev_begin));
-    BSFM_CUDA_TRY(cudaEventCreate(&ev_end));
-    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } eguard{ev_begin, ev_end};
+    cudaEvent_t ev_begin = ctx.ev_begin, ev_end = ctx.ev_end;
     BSFM_CUDA_TRY(cudaEventRecord(ev_begin, st));
     g_timing = Timing();
 
@@ -407,14 +420,10 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     BSFM_CUDA_TRY(cudaMemsetAsync(P.ticket, 0, 4 * sizeof(unsigned int), st));
     TRY(D.alloc(&P.sc, 1));
     BSFM_CUDA_TRY(cudaMemsetAsync(P.sc, 0, sizeof(Scalars), st));
-    double *d_mu, *h_mu = nullptr;
+    double *d_mu, *h_mu = ctx.h_mu;
     TRY(D.alloc(&d_mu, 1));
     P.mu = d_mu;
-    BSFM_CUDA_TRY(cudaMallocHost(&h_mu, sizeof(double)));
-    struct HostGuard2 { void *p; ~HostGuard2() { cudaFreeHost(p); } } hguard2{h_mu};
-    Scalars *h_sc = nullptr;
-    BSFM_CUDA_TRY(cudaMallocHost(&h_sc, sizeof(Scalars)));
-    struct HostGuard { void *p; ~HostGuard() { cudaFreeHost(p); } } hguard{h_sc};
+    Scalars *h_sc = ctx.h_sc;
     BSFM_CUDA_TRY(cudaMemcpyAsync(d_p, p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));
     PT.end();
 

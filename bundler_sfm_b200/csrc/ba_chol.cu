@@ -190,7 +190,12 @@ __global__ void __launch_bounds__(256) chol_syrk_dmma_kernel(double *A, const do
 // Row block index nbk (= one row) is the right-hand side carried along as matrix row n.
 // (loops over shared memory, not unrolled register code: a kernel that runs ~10 us must not spend it
 // fetching tens of KB of straight-line instructions)
-__global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout, int ld, int n, int k, int cend, double *Linv_all, Scalars *sc)
+#ifndef BSFM_CHOL_STEP_THREADS
+#define BSFM_CHOL_STEP_THREADS 512
+#endif
+constexpr int CST = BSFM_CHOL_STEP_THREADS;      // threads of chol_step_kernel (8 or 16 warps)
+constexpr int CSW = CST / 32;
+__global__ void __launch_bounds__(CST) chol_step_kernel(double *A, double *Lout, int ld, int n, int k, int cend, double *Linv_all, Scalars *sc)
 {
     __shared__ double Lk[NB][NB + 1];
     __shared__ double Xr[NB][NB + 1];
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
 
     DBG_T(0);
     if (tid == 0) fail_s = 0;
-    for (int e = tid; e < NB * NB; e += 256) {
+    for (int e = tid; e < NB * NB; e += CST) {
         const int r = e >> 5, c = e & 31;
         Lk[r][c] = (r < nb && c <= r) ? A[(size_t) (k0 + r) * ld + (k0 + c)] : ((r == c) ? 1.0 : 0.0);
         Xr[r][c] = (r < rrows && c < nb) ? A[(size_t) (rbase + r) * ld + (k0 + c)] : 0.0;
@@ -255,8 +260,8 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
         const double xjr = xr * rinv, xjc = xc * rinv;
         if (tid == 0) { dinv[j] = rinv; if (bad) fail_s = 1; }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int c = warp + 8 * q;                      // warp-uniform
+        for (int q = 0; q < NB / CSW; q++) {
+            const int c = warp + CSW * q;                    // warp-uniform
             if (c > j && c < nb) {
                 const double lc = __shfl_sync(0xffffffffu, l, c);   // L[c][j]
                 if (lane >= c) Lk[lane][c] = fma(-l, lc, Lk[lane][c]);
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
     __syncthreads();
     DBG_T(2);
     // rescale: L[r][c] = a_rc dinv[c] (c < r), L[c][c] = d_c dinv[c], X[r][c] *= dinv[c]
-    for (int e = tid; e < NB * NB; e += 256) {
+    for (int e = tid; e < NB * NB; e += CST) {
         const int r = e >> 5, c = e & 31;
         const double sc_c = dinv[c];
         if (c <= r && r < nb) Lk[r][c] *= sc_c;
@@ -285,13 +290,13 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
     __syncthreads();
     DBG_T(3);
     if (owner) {   // Z = L_kk^-1 = Xc^T (lower triangular)
-        for (int e = tid; e < NB * NB; e += 256) { const int r = e >> 5, c = e & 31; Linv_all[(size_t) k * NB * NB + e] = (c <= r) ? Xc[c][r] : 0.0; }
+        for (int e = tid; e < NB * NB; e += CST) { const int r = e >> 5, c = e & 31; Linv_all[(size_t) k * NB * NB + e] = (c <= r) ? Xc[c][r] : 0.0; }
     }
     // panel write-back goes to the SEPARATE factor matrix Lout: other CTAs of this launch (possibly in a later
     // wave) still read the un-solved panel blocks from A, so A's panel columns must not change during the step.
     // The owner writes the RHS segment, first-column tiles write their row block
     if (writeback) {
-        for (int e = tid; e < NB * NB; e += 256) {
+        for (int e = tid; e < NB * NB; e += CST) {
             const int r = e >> 5, c = e & 31;
             if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
         }
@@ -300,8 +305,8 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double *A, double *Lout,
     // trailing tile (rb, cb):  A[r][c] -= sum_t Xr[r][t] Xc[c][t]   (c <= r on the diagonal tile)
     const double (*XC)[NB + 1] = need_c ? Xc : Xr;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int e = tid + q * 256;
+    for (int q = 0; q < NB * NB / CST; q++) {
+        const int e = tid + q * CST;
         const int r = e >> 5, c = e & 31;
         if (r < rrows && c < crows && (rb != cb || c <= r)) {
             double acc = 0.0;
@@ -468,12 +473,12 @@ int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws,
             const int extra = (k + 1 >= cend) ? (nbk - 1 - k) : 0;
             if (tiles + extra > 800) {
                 // many more tiles than resident CTAs: factor the diagonal block once, then the GEMM-style tile kernel
-                chol_step_kernel<<<1, 256, 0, st>>>(A, Lmat, ld, n, k, k + 1, linv_ws, sc);
+                chol_step_kernel<<<1, CST, 0, st>>>(A, Lmat, ld, n, k, k + 1, linv_ws, sc);
                 BSFM_KERNEL_CHECK();
                 chol_tile_kernel<<<tiles + extra, 256, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws);
                 BSFM_KERNEL_CHECK();
             } else {
-                chol_step_kernel<<<1 + tiles + extra, 256, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws, sc);
+                chol_step_kernel<<<1 + tiles + extra, CST, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws, sc);
                 BSFM_KERNEL_CHECK();
             }
         }

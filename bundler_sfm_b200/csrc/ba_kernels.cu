@@ -577,8 +577,17 @@ __global__ void vinv_kernel(Problem P)
 // order) is cut into chunks of SCHUR_CHUNK tuples.  Pass A: one warp per chunk accumulates a partial
 // 9x9 (+ 9 for E on diagonal blocks).  Pass B: one warp per block adds its chunks in order and writes
 // S (both triangles) and E.  Fixed shapes and orders => bitwise reproducible.
-// Lane l < 27 owns Y element (l/3, l%3); the 81 block entries are spread 3 per lane, fed by shuffles.
 // ------------------------------------------------------------------------------------------------
+// The 9x3 . 3x9 products run on the fp64 tensor cores: Y_ij (rows padded to 16, K padded to 4) is the A
+// operand of mma.sync.m8n8k4.f64, W_ik^T the B operand; column 9 of the second n-tile carries eb_i, so the
+// E_j partial sum comes out of the same instruction.  Every lane forms its own fragment elements straight
+// from global memory (the 27-double blocks are L1-resident), so there are no shuffles.
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
 {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -593,63 +602,62 @@ __global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
     const bool diag = (key / (uint32_t) m) == (key % (uint32_t) m);
     const int t0 = P.blk_start[b] + (c - P.chunk_off[b]) * SCHUR_CHUNK;
     const int t1 = min(t0 + SCHUR_CHUNK, P.blk_start[b + 1]);
-    const int nY = cnp * 3, nn = cnp * cnp;
-    const int yr = (lane < nY ? lane : 0) / 3, yc = lane % 3;
-    const int q0 = lane, q1 = lane + 32, q2 = lane + 64;
-    const int i0 = (q0 < nn ? q0 : 0) / cnp, j0 = (q0 < nn ? q0 : 0) % cnp;
-    const int i1 = (q1 < nn ? q1 : 0) / cnp, j1 = (q1 < nn ? q1 : 0) % cnp;
-    const int i2 = (q2 < nn ? q2 : 0) / cnp, j2 = (q2 < nn ? q2 : 0) % cnp;
-    const int er = lane < cnp ? lane : 0;
+    const int nY = cnp * 3;
+    const int g = lane >> 2, tg = lane & 3;
+    const bool kv = tg < 3;                       // K = 3 padded to 4
+    const bool r0v = kv && g < cnp;               // A rows 0..7
+    const bool r1v = kv && 8 + g < cnp;           // A rows 8..15 (only row 8 exists for cnp = 9)
+    const bool c0v = kv && g < cnp;               // B cols 0..7
+    const bool c1v = kv && 8 + g < cnp;           // B cols 8..15
+    const bool ev = kv && diag && g == 1;         // B col 9 <- eb_i
     const double *eb = P.eab + (size_t) m * cnp;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, accE = 0.0;
+    double a00[2] = {0, 0}, a01[2] = {0, 0}, a10[2] = {0, 0}, a11[2] = {0, 0};
 
-    // software pipeline: operands of tuple t+1 are in flight while tuple t is reduced
-    double wa0 = 0, wa1 = 0, wa2 = 0, v0 = 0, v1 = 0, v2 = 0, wb = 0, ebv = 0;
+    // operands of tuple t+1 are in flight while tuple t is multiplied
+    double wa0[3] = {0, 0, 0}, wa1[3] = {0, 0, 0}, vi[3] = {0, 0, 0}, b0 = 0, b1 = 0;
     auto load = [&](int t) {
         const int4 tp = P.tuples[t];
-        if (lane < nY) {
-            const double *Wa = P.W + (size_t) tp.x * nY + yr * 3;
-            const double *Vi = P.Vinv + (size_t) tp.z * 9 + yc;
-            wa0 = Wa[0]; wa1 = Wa[1]; wa2 = Wa[2];
-            v0 = Vi[0]; v1 = Vi[3]; v2 = Vi[6];
-            wb = P.W[(size_t) tp.y * nY + lane];
-        }
-        if (diag && lane < 3) ebv = eb[(size_t) tp.z * 3 + lane];
+        const double *Wa = P.W + (size_t) tp.x * nY;
+        const double *Wb = P.W + (size_t) tp.y * nY;
+        const double *Vi = P.Vinv + (size_t) tp.z * 9;
+        if (kv) { vi[0] = Vi[tg]; vi[1] = Vi[3 + tg]; vi[2] = Vi[6 + tg]; }
+        if (r0v) { wa0[0] = Wa[g * 3]; wa0[1] = Wa[g * 3 + 1]; wa0[2] = Wa[g * 3 + 2]; }
+        if (r1v) { wa1[0] = Wa[(8 + g) * 3]; wa1[1] = Wa[(8 + g) * 3 + 1]; wa1[2] = Wa[(8 + g) * 3 + 2]; }
+        b0 = c0v ? Wb[g * 3 + tg] : 0.0;
+        b1 = c1v ? Wb[(8 + g) * 3 + tg] : (ev ? eb[(size_t) tp.z * 3 + tg] : 0.0);
     };
     if (t0 < t1) load(t0);
     for (int t = t0; t < t1; t++) {
-        // Y[yr][yc] = sum_c Wa[yr][c] * Vinv[c][yc]   (sba_levmar.c:1206-1214)
-        double y = 0.0;
-        y += wa0 * v0; y += wa1 * v1; y += wa2 * v2;
-        const double wbc = wb, ebc = ebv;
+        // Y[row][tg] = sum_c Wa[row][c] * Vinv[c][tg]   (sba_levmar.c:1206-1214)
+        double y0 = 0.0, y1 = 0.0;
+        y0 += wa0[0] * vi[0]; y0 += wa0[1] * vi[1]; y0 += wa0[2] * vi[2];
+        y1 += wa1[0] * vi[0]; y1 += wa1[1] * vi[1]; y1 += wa1[2] * vi[2];
+        if (!r0v) y0 = 0.0;
+        if (!r1v) y1 = 0.0;
+        const double bb0 = b0, bb1 = b1;
         if (t + 1 < t1) load(t + 1);
-        // YWt[ii][jj] += sum_l Y[ii][l] * Wb[jj][l]      (sba_levmar.c:1262-1275)
-        {
-            double s = 0.0;
+        // YWt += Y W_ik^T  (sba_levmar.c:1262-1275), E partial in column 9 (:1318-1333)
+        dmma884(a00[0], a00[1], y0, bb0);
+        dmma884(a01[0], a01[1], y0, bb1);
+        dmma884(a10[0], a10[1], y1, bb0);
+        dmma884(a11[0], a11[1], y1, bb1);
+    }
+    // accumulator element (row = g, col = 2 tg + e) of tile (mt, nt) -> entry (mt*8 + g, nt*8 + 2 tg + e)
+    double *out = P.schur_part + (size_t) c * SCHUR_PART_STRIDE;
 #pragma unroll
-            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, i0 * 3 + l) * __shfl_sync(0xffffffffu, wbc, j0 * 3 + l);
-            acc0 += s;
-            s = 0.0;
-#pragma unroll
-            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, i1 * 3 + l) * __shfl_sync(0xffffffffu, wbc, j1 * 3 + l);
-            acc1 += s;
-            s = 0.0;
-#pragma unroll
-            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, i2 * 3 + l) * __shfl_sync(0xffffffffu, wbc, j2 * 3 + l);
-            acc2 += s;
+    for (int e = 0; e < 2; e++) {
+        const int col0 = 2 * tg + e, col1 = 8 + 2 * tg + e;
+        if (g < cnp) {
+            if (col0 < cnp) out[g * cnp + col0] = a00[e];
+            if (col1 < cnp) out[g * cnp + col1] = a01[e];
+            else if (diag && col1 == 9) out[81 + g] = a01[e];
         }
-        if (diag) {   // E_j partial: sum_i Y_ij eb_i (sba_levmar.c:1318-1333); lane ii < cnp owns row ii
-            double s = 0.0;
-#pragma unroll
-            for (int l = 0; l < 3; l++) s += __shfl_sync(0xffffffffu, y, er * 3 + l) * __shfl_sync(0xffffffffu, ebc, l);
-            accE += s;
+        if (8 + g < cnp) {
+            if (col0 < cnp) out[(8 + g) * cnp + col0] = a10[e];
+            if (col1 < cnp) out[(8 + g) * cnp + col1] = a11[e];
+            else if (diag && col1 == 9) out[81 + 8 + g] = a11[e];
         }
     }
-    double *out = P.schur_part + (size_t) c * SCHUR_PART_STRIDE;
-    if (q0 < nn) out[q0] = acc0;
-    if (q1 < nn) out[q1] = acc1;
-    if (q2 < nn) out[q2] = acc2;
-    if (diag && lane < cnp) out[81 + lane] = accE;
 }
 
 __global__ void __launch_bounds__(128) schur_final_kernel(Problem P)

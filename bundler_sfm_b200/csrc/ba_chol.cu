@@ -205,6 +205,9 @@ __global__ void __launch_bounds__(CST) chol_step_kernel(double *A, double *Lout,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nbk = (n + NB - 1) / NB;           // matrix row blocks; block nbk = RHS row
     const int k0 = k * NB, nb = min(NB, n - k0);
+    // programmatic dependent launch: this grid may be scheduled while its predecessor drains; nothing the
+    // predecessor wrote is touched before this point
+    cudaGridDependencySynchronize();
     // tile of this CTA: blockIdx 0 = panel owner (no tile); else (cb, rb), k < cb <= rb <= nbk, cb < cend <= nbk
     // (cend < nbk: only the columns of the current outer panel are updated here; the rest of the trailing matrix
     //  is updated once per outer panel by the DMMA SYRK kernel)
@@ -403,6 +406,7 @@ __global__ void __launch_bounds__(512) chol_backsolve_blocked_kernel(const doubl
     __shared__ double ys[NB];
     __shared__ double Li[NB][NB + 1];
     const int tid = threadIdx.x;
+    cudaGridDependencySynchronize();
     const double *yrow = A + (size_t) n * ld;
     // y lives in registers for the first 512 columns per thread and in `ywork` (global) beyond that
     double y0 = (tid < n) ? yrow[tid] : 0.0;
@@ -464,6 +468,7 @@ int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws,
     // panel's own columns; the rest of the trailing matrix gets ONE K = NBO update on the fp64 tensor cores.
     // Small systems (latency-bound) use a single outer panel = the whole matrix.
     const int NBO = (n > 1536) ? 256 : nbk * NB;
+    static const bool use_pdl = getenv("BSFM_BA_NO_PDL") == nullptr;
     for (int K0 = 0; K0 < n; K0 += NBO) {
         const int K1 = min(n, K0 + NBO);
         const int cend = (K1 + NB - 1) / NB;
@@ -478,8 +483,8 @@ int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws,
                 chol_tile_kernel<<<tiles + extra, 256, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws);
                 BSFM_KERNEL_CHECK();
             } else {
-                chol_step_kernel<<<1 + tiles + extra, CST, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws, sc);
-                BSFM_KERNEL_CHECK();
+                if (use_pdl) { BSFM_CUDA_TRY(launch_pdl(chol_step_kernel, dim3(1 + tiles + extra), dim3(CST), st, A, Lmat, ld, n, k, cend, linv_ws, sc)); count_launch(); }
+                else { chol_step_kernel<<<1 + tiles + extra, CST, 0, st>>>(A, Lmat, ld, n, k, cend, linv_ws, sc); BSFM_KERNEL_CHECK(); }
             }
         }
         if (K1 < n) {
@@ -490,8 +495,8 @@ int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws,
             BSFM_KERNEL_CHECK();
         }
     }
-    chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, ld, n, linv_ws, x, ywork);
-    BSFM_KERNEL_CHECK();
+    if (use_pdl) { BSFM_CUDA_TRY(launch_pdl(chol_backsolve_blocked_kernel, dim3(1), dim3(512), st, (const double *) Lmat, ld, n, (const double *) linv_ws, x, ywork)); count_launch(); }
+    else { chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, ld, n, linv_ws, x, ywork); BSFM_KERNEL_CHECK(); }
     return BSFM_OK;
 }
 

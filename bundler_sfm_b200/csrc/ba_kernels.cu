@@ -162,6 +162,7 @@ __device__ __forceinline__ void load_cam(const Problem &P, const double *p, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void cam_prep_kernel(Problem P, const double *p, int with_pert)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.m) return;
     const double *a = p + (size_t) j * P.M.cnp;
@@ -187,6 +188,7 @@ __global__ void cam_prep_kernel(Problem P, const double *p, int with_pert)
 // ------------------------------------------------------------------------------------------------
 __global__ void residual_kernel(Problem P, const double *p, double *e_out, const double *e_prev, double eps5)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0, pct = 0.0;
     if (o < P.nvis) {
@@ -299,6 +301,7 @@ __device__ __forceinline__ void analytic_jac(const Problem &P, const double (&a)
 
 __global__ void __launch_bounds__(128) jacobian_kernel(Problem P, const double *p, int jac_mode)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= P.nvis) return;
     const Model &M = P.M;
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(128) jacobian_kernel(Problem P, const double *
 // ------------------------------------------------------------------------------------------------
 __global__ void v_kernel(Problem P, const double *p, const double *e)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     double V[6] = {0, 0, 0, 0, 0, 0};   // 00 01 02 11 12 22
@@ -418,6 +422,7 @@ constexpr int U_THREADS = 128;
 // pass 1: CTA (j, seg) accumulates the seg-th slice of camera j's observations -> Upart[j][seg][54]
 __global__ void __launch_bounds__(U_THREADS) u_partial_kernel(Problem P, const double *e, int nseg)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int j = blockIdx.x / nseg, seg = blockIdx.x % nseg;
     const int cnp = P.M.cnp;
     double acc[54];   // 45 upper-triangular U entries (row-major) + 9 ea
@@ -461,6 +466,7 @@ __global__ void __launch_bounds__(U_THREADS) u_partial_kernel(Problem P, const d
 // pass 2: combine the segments in order, scatter to U_j (full symmetric) and ea_j, add constraints
 __global__ void __launch_bounds__(96) u_final_kernel(Problem P, const double *p, int nseg)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     __shared__ double sm[54];
     const int j = blockIdx.x;
     const int cnp = P.M.cnp;
@@ -499,6 +505,7 @@ __global__ void __launch_bounds__(96) u_final_kernel(Problem P, const double *p,
 // ------------------------------------------------------------------------------------------------
 __global__ void grad_stats_kernel(Problem P, const double *p)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int cnp = P.M.cnp;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     double inf = 0.0, pl2 = 0.0, md = DBL_MIN;
@@ -521,6 +528,7 @@ __global__ void grad_stats_kernel(Problem P, const double *p)
 
 __global__ void penalty_kernel(Problem P, const double *p)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     // evaluated by one thread in the reference's order (small: m*cnp + constrained points)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int cnp = P.M.cnp;
@@ -549,6 +557,7 @@ __global__ void penalty_kernel(Problem P, const double *p)
 // ------------------------------------------------------------------------------------------------
 __global__ void vinv_kernel(Problem P)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const double mu = *P.mu;
@@ -590,6 +599,7 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 __global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= P.nchunks) return;
@@ -662,6 +672,7 @@ __global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
 
 __global__ void __launch_bounds__(128) schur_final_kernel(Problem P)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= P.nblocks) return;
@@ -710,6 +721,7 @@ __global__ void __launch_bounds__(128) schur_final_kernel(Problem P)
 // zero the dense S (blocks of camera pairs with no common point stay zero)
 __global__ void zero_kernel(double *ptr, size_t count)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t) gridDim.x * blockDim.x;
     for (; q < count; q += stride) ptr[q] = 0.0;
@@ -721,6 +733,7 @@ __global__ void zero_kernel(double *ptr, size_t count)
 // ------------------------------------------------------------------------------------------------
 __global__ void backsub_kernel(Problem P, const double *da)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int cnp = P.M.cnp;
     if (i < P.m * cnp) {
@@ -758,6 +771,7 @@ __global__ void backsub_kernel(Problem P, const double *da)
 // ------------------------------------------------------------------------------------------------
 __global__ void update_kernel(Problem P, const double *p, double *pdp)
 {
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const double mu = *P.mu;
     double d2 = 0.0, dl = 0.0;

@@ -87,5 +87,20 @@ struct Problem {
     const double *mu; // damping term of the current try (device scalar, written by the host)
 };
 
+// launch with the programmatic-stream-serialization attribute (PDL): the launch latency of a kernel overlaps
+// the tail of its predecessor; every kernel launched this way calls cudaGridDependencySynchronize() before it
+// reads anything its predecessors wrote
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace ba
 }  // namespace bsfm

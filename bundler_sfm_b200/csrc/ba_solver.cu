@@ -155,6 +155,13 @@ struct PhaseTimer {
 }  // namespace
 
 #define TRY(expr) do { int rc__ = (expr); if (rc__ != BSFM_OK) return rc__; } while (0)
+// PDL launch of a BA kernel on stream `st` (plain launch when BSFM_BA_NO_PDL is set)
+#define BA_LAUNCH(kernel, grid, block, ...)                                                              \
+    do {                                                                                                \
+        if (use_pdl) BSFM_CUDA_TRY(launch_pdl(kernel, dim3(grid), dim3(block), st, __VA_ARGS__));       \
+        else kernel<<<(grid), (block), 0, st>>>(__VA_ARGS__);                                          \
+        BSFM_KERNEL_CHECK();                                                                            \
+    } while (0)
 
 extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,
                                             const double *x, const double *covx, int mnp,
@@ -183,6 +190,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         if (jm && !strcmp(jm, "fd")) jac_mode = BSFM_BA_JAC_FD;
     }
     { int dev = 0; BSFM_CUDA_TRY(cudaGetDevice(&dev)); g_pool.bind_device(dev); }
+    static const bool use_pdl = getenv("BSFM_BA_NO_PDL") == nullptr;
     const long long launches0 = g_kernel_launches.load();
     // stream, events and the pinned scalar blocks are created once per thread and device and reused: driver
     // calls that allocate (cudaMallocHost, cudaStreamCreate, ...) serialise on a global lock and cost more than
@@ -435,10 +443,8 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     const int with_pert = (jac_mode == BSFM_BA_JAC_FD) ? 1 : 0;
     auto launch_residual = [&](const double *pp, double *camR, double *eout, const double *eprev, double eps5v) -> int {
         P.camR = camR;
-        cam_prep_kernel<<<(m + 127) / 128, 128, 0, st>>>(P, pp, with_pert);
-        BSFM_KERNEL_CHECK();
-        residual_kernel<<<red_blocks_obs, 256, 0, st>>>(P, pp, eout, eprev, eps5v);
-        BSFM_KERNEL_CHECK();
+        BA_LAUNCH(cam_prep_kernel, (m + 127) / 128, 128, P, pp, with_pert);
+        BA_LAUNCH(residual_kernel, red_blocks_obs, 256, P, pp, eout, eprev, eps5v);
         return BSFM_OK;
     };
 
@@ -452,7 +458,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
 
     PT.begin(4);
     TRY(launch_residual(d_p, d_camR_a, d_e, nullptr, 0.0)); nfev = 1;
-    if (any_constraints) { penalty_kernel<<<1, 32, 0, st>>>(P, d_p); BSFM_KERNEL_CHECK(); }
+    if (any_constraints) { BA_LAUNCH(penalty_kernel, 1, 32, P, d_p); BSFM_KERNEL_CHECK(); }
     PT.end();
     TRY(read_scalars());
     pen = any_constraints ? h_sc->penalty : 0.0;
@@ -467,14 +473,10 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         jacobian_kernel<<<(nvis + 127) / 128, 128, 0, st>>>(P, d_p, jac_mode); ++njev;
         BSFM_KERNEL_CHECK();
         u_partial_kernel<<<m * useg, 128, 0, st>>>(P, d_e, useg);
-        BSFM_KERNEL_CHECK();
-        u_final_kernel<<<m, 96, 0, st>>>(P, d_p, useg);
-        BSFM_KERNEL_CHECK();
-        v_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, d_p, d_e);
-        BSFM_KERNEL_CHECK();
+        BA_LAUNCH(u_final_kernel, m, 96, P, d_p, useg);
+        BA_LAUNCH(v_kernel, (n + 127) / 128, 128, P, d_p, d_e);
         if (Vout) BSFM_CUDA_TRY(cudaMemcpyAsync(Vout, P.V, (size_t) n * 9 * sizeof(double), cudaMemcpyDefault, st));   // :1039-1051
-        grad_stats_kernel<<<red_blocks_var, 256, 0, st>>>(P, d_p);
-        BSFM_KERNEL_CHECK();
+        BA_LAUNCH(grad_stats_kernel, red_blocks_var, 256, P, d_p);
         PT.end();
         TRY(read_scalars());
         eab_inf = h_sc->eab_inf; p_L2 = h_sc->p_L2; max_diag = h_sc->max_diag;
@@ -488,25 +490,19 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
             *h_mu = mu;
             BSFM_CUDA_TRY(cudaMemcpyAsync(d_mu, h_mu, sizeof(double), cudaMemcpyHostToDevice, st));
             PT.begin(2);
-            vinv_kernel<<<(n + 255) / 256, 256, 0, st>>>(P);
-            BSFM_KERNEL_CHECK();
+            BA_LAUNCH(vinv_kernel, (n + 255) / 256, 256, P);
             if (!s_dense) {   // camera pairs without a common point keep S_jk = 0
-                zero_kernel<<<std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, 0, st>>>(P.S, (size_t) Sdim * Sdim);
-                BSFM_KERNEL_CHECK();
+                BA_LAUNCH(zero_kernel, std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, P.S, (size_t) Sdim * Sdim);
             }
-            schur_partial_kernel<<<(nchunks * 32 + 127) / 128, 128, 0, st>>>(P);
-            BSFM_KERNEL_CHECK();
-            schur_final_kernel<<<(nblocks * 32 + 127) / 128, 128, 0, st>>>(P);
-            BSFM_KERNEL_CHECK();
+            BA_LAUNCH(schur_partial_kernel, (nchunks * 32 + 127) / 128, 128, P);
+            BA_LAUNCH(schur_final_kernel, (nblocks * 32 + 127) / 128, 128, P);
             PT.end();
             PT.begin(3);
             TRY(chol_solve(st, P.S, d_Lmat, Sdim, d_linv, d_da, P.sc));
             PT.end();
             PT.begin(4);
-            backsub_kernel<<<(std::max(n, m * cnp) + 127) / 128, 128, 0, st>>>(P, d_da);
-            BSFM_KERNEL_CHECK();
-            update_kernel<<<red_blocks_var, 256, 0, st>>>(P, d_p, d_pdp);
-            BSFM_KERNEL_CHECK();
+            BA_LAUNCH(backsub_kernel, (std::max(n, m * cnp) + 127) / 128, 128, P, d_da);
+            BA_LAUNCH(update_kernel, red_blocks_var, 256, P, d_p, d_pdp);
             TRY(launch_residual(d_pdp, d_camR_b, d_enew, d_e, eps5));
             PT.end();
             TRY(read_scalars());
@@ -550,7 +546,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
                         if (max_pct_change < eps5 && itno >= 4) { stop = 8; break; }               // :1569-1572 (step discarded)
                         std::swap(d_p, d_pdp); std::swap(d_e, d_enew); std::swap(d_camR_a, d_camR_b);
                         p_eL2 = pdp_eL2;
-                        if (any_constraints) { penalty_kernel<<<1, 32, 0, st>>>(P, d_p); BSFM_KERNEL_CHECK(); }
+                        if (any_constraints) { BA_LAUNCH(penalty_kernel, 1, 32, P, d_p); BSFM_KERNEL_CHECK(); }
                         take_moredamping = false;
                     }
                 }
@@ -576,11 +572,8 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         jacobian_kernel<<<(nvis + 127) / 128, 128, 0, st>>>(P, d_p, jac_mode); ++njev;
         BSFM_KERNEL_CHECK();
         u_partial_kernel<<<m * useg, 128, 0, st>>>(P, d_e, useg);
-        BSFM_KERNEL_CHECK();
-        u_final_kernel<<<m, 96, 0, st>>>(P, d_p, useg);
-        BSFM_KERNEL_CHECK();
-        v_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, d_p, d_e);
-        BSFM_KERNEL_CHECK();
+        BA_LAUNCH(u_final_kernel, m, 96, P, d_p, useg);
+        BA_LAUNCH(v_kernel, (n + 127) / 128, 128, P, d_p, d_e);
         if (Uout) BSFM_CUDA_TRY(cudaMemcpyAsync(Uout, P.U, (size_t) m * cnp * cnp * sizeof(double), cudaMemcpyDefault, st));
         if (Vout) BSFM_CUDA_TRY(cudaMemcpyAsync(Vout, P.V, (size_t) n * 9 * sizeof(double), cudaMemcpyDefault, st));
         vinv_export_kernel<<<(n + 255) / 256, 256, 0, st>>>(P);
@@ -595,12 +588,9 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         }
         *h_mu = 0.0;
         BSFM_CUDA_TRY(cudaMemcpyAsync(d_mu, h_mu, sizeof(double), cudaMemcpyHostToDevice, st));
-        zero_kernel<<<std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, 0, st>>>(P.S, (size_t) Sdim * Sdim);
-        BSFM_KERNEL_CHECK();
-        schur_partial_kernel<<<(nchunks * 32 + 127) / 128, 128, 0, st>>>(P);
-        BSFM_KERNEL_CHECK();
-        schur_final_kernel<<<(nblocks * 32 + 127) / 128, 128, 0, st>>>(P);
-        BSFM_KERNEL_CHECK();
+        BA_LAUNCH(zero_kernel, std::min(1024, (int) (((size_t) Sdim * Sdim + 255) / 256)), 256, P.S, (size_t) Sdim * Sdim);
+        BA_LAUNCH(schur_partial_kernel, (nchunks * 32 + 127) / 128, 128, P);
+        BA_LAUNCH(schur_final_kernel, (nblocks * 32 + 127) / 128, 128, P);
         BSFM_CUDA_TRY(cudaMemcpyAsync(Sout, P.S, (size_t) Sdim * Sdim * sizeof(double), cudaMemcpyDefault, st));   // symmetric: transpose == itself (:2017-2025)
     }
     BSFM_CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));

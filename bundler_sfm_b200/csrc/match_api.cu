@@ -4,6 +4,7 @@
 #include "common.h"
 #include "match_kernels.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -13,12 +14,13 @@
 namespace bsfm {
 namespace match {
 // kernels (match_kernels.cu)
-__global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, const int32_t *, uint8_t *, int32_t *, int64_t);
+__global__ void raw_norm_kernel(const uint8_t *, int64_t, int32_t *, int32_t *);
+__global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, const int32_t *, const int32_t *, const int32_t *, uint8_t *, int32_t *, int32_t *, int64_t);
 __global__ void match_dp4a_kernel(MatchParams);
 __global__ void match_tc_kernel(MatchParams);
 __global__ void match_verify_kernel(MatchParams, int);
 __global__ void match_finalize_kernel(const uint32_t *, const int32_t *, int, const RunImage *, int, int,
-                                      const int32_t *, const int32_t *, int32_t *, int32_t *);
+                                      const int32_t *, const int32_t *, const int32_t *, int32_t *, int32_t *);
 }  // namespace match
 }  // namespace bsfm
 
@@ -34,6 +36,7 @@ struct bsfm_keydb {
     int64_t drows = 0;
     uint8_t *d_keys_sw = nullptr;
     int32_t *d_norms = nullptr;
+    int32_t *d_perm = nullptr;
     int32_t *d_tile_img = nullptr;
     int32_t *d_img_doff = nullptr;
     cudaStream_t stream = nullptr;
@@ -92,6 +95,7 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
     for (int e = 0; e < 4; e++) BSFM_CUDA_TRY(cudaEventCreate(&db->ev[e]));
     BSFM_CUDA_TRY(cudaMalloc(&db->d_keys_sw, (size_t) db->drows * DESC_BYTES));
     BSFM_CUDA_TRY(cudaMalloc(&db->d_norms, (size_t) db->drows * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_perm, (size_t) db->drows * sizeof(int32_t)));
     BSFM_CUDA_TRY(cudaMalloc(&db->d_tile_img, (size_t) ntiles * sizeof(int32_t)));
     BSFM_CUDA_TRY(cudaMalloc(&db->d_img_doff, (size_t) (N + 1) * sizeof(int32_t)));
     BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_tile_img, tile_img.data(), (size_t) ntiles * sizeof(int32_t), cudaMemcpyHostToDevice, db->stream));
@@ -108,16 +112,38 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
         BSFM_CUDA_TRY(cudaMalloc(&d_raw, (size_t) total_keys * DESC_BYTES));
         BSFM_CUDA_TRY(cudaMemcpyAsync(d_raw, keys, (size_t) total_keys * DESC_BYTES, cudaMemcpyHostToDevice, db->stream));
     }
+    // per-image stable sort of the keys by squared norm (the tensor-core epilogue relies on norm-sorted chunks)
+    int32_t *d_nraw = nullptr, *d_nsorted = nullptr, *d_iota = nullptr, *d_src = nullptr, *d_seg = nullptr;
+    void *d_tmp = nullptr;
+    if (total_keys > (int64_t) INT_MAX - 1) { set_error("bsfm_keydb_create: more than 2^31 keys"); return BSFM_ERR_ARG; }
+    const size_t nk = (size_t) std::max<int64_t>(total_keys, 1);
+    BSFM_CUDA_TRY(cudaMalloc(&d_nraw, nk * 4)); BSFM_CUDA_TRY(cudaMalloc(&d_nsorted, nk * 4));
+    BSFM_CUDA_TRY(cudaMalloc(&d_iota, nk * 4)); BSFM_CUDA_TRY(cudaMalloc(&d_src, nk * 4));
+    BSFM_CUDA_TRY(cudaMalloc(&d_seg, (size_t) (N + 1) * 4));
+    if (total_keys > 0) {
+        std::vector<int32_t> seg((size_t) N + 1);
+        for (int i = 0; i <= N; i++) seg[(size_t) i] = (int32_t) key_off[i];
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_seg, seg.data(), (size_t) (N + 1) * 4, cudaMemcpyHostToDevice, db->stream));
+        raw_norm_kernel<<<(unsigned) ((total_keys + 7) / 8), 256, 0, db->stream>>>(d_raw, total_keys, d_nraw, d_iota);
+        BSFM_KERNEL_CHECK();
+        size_t tb = 0;
+        cub::DeviceSegmentedSort::StableSortPairs(nullptr, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, N, d_seg, d_seg + 1, db->stream);
+        BSFM_CUDA_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tb, 1)));
+        cub::DeviceSegmentedSort::StableSortPairs(d_tmp, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, N, d_seg, d_seg + 1, db->stream);
+        count_launch(3);
+        BSFM_CUDA_TRY(cudaGetLastError());
+        BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));   // seg[] is a host temporary
+    }
     {
         const int warps_per_block = 8;
         const int64_t blocks = (db->drows + warps_per_block - 1) / warps_per_block;
-        prep_kernel<<<(unsigned) blocks, warps_per_block * 32, 0, db->stream>>>(d_raw, d_key_off, db->d_img_doff, db->d_tile_img,
-                                                                                 db->d_keys_sw, db->d_norms, db->drows);
+        prep_kernel<<<(unsigned) blocks, warps_per_block * 32, 0, db->stream>>>(d_raw, d_key_off, db->d_img_doff, db->d_tile_img, d_src, d_nsorted,
+                                                                                 db->d_keys_sw, db->d_norms, db->d_perm, db->drows);
         BSFM_KERNEL_CHECK();
     }
     BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
     if (!keys_on_device && d_raw) cudaFree(d_raw);
-    cudaFree(d_key_off);
+    cudaFree(d_key_off); cudaFree(d_nraw); cudaFree(d_nsorted); cudaFree(d_iota); cudaFree(d_src); cudaFree(d_seg); cudaFree(d_tmp);
     return BSFM_OK;
 }
 
@@ -206,7 +232,9 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     // ---- chunked launches ---------------------------------------------------------------------
     const int64_t chunk_slots = std::max(1, env_int("BSFM_MATCH_CHUNK_MSLOTS", 32)) * (int64_t) (1 << 20);
     const int64_t chunk_units = std::max<int64_t>(1, chunk_slots / TILE_Q);
-    const int64_t max_units = std::min<int64_t>(chunk_units, nunits);
+    int64_t biggest_img = 1;
+    for (const RunImage &R : run) biggest_img = std::max<int64_t>(biggest_img, R.nunits);
+    const int64_t max_units = std::min<int64_t>(std::max(chunk_units, biggest_img), nunits);
     const int64_t cap = max_units * TILE_Q;   // worst case: every query row is a candidate / match
 
     // scratch carve-up
@@ -228,6 +256,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
 
     MatchParams P;
     P.keys_sw = db->d_keys_sw; P.norms = db->d_norms; P.run_imgs = d_run; P.num_run_imgs = K;
+    P.perm = db->d_perm; P.tile_img = db->d_tile_img; P.img_doff = db->d_img_doff;
     P.ratio_sq = ratio * ratio;
     P.neg2 = -2;
     P.cand = (int32_t *) (S + o_cand); P.cand_cap = (int32_t) cap;
@@ -241,8 +270,14 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     }
 
     float ms_search = 0.f;
-    for (int64_t u0 = 0; u0 < nunits; u0 += chunk_units) {
-        const int64_t u1 = std::min(nunits, u0 + chunk_units);
+    // launches cover whole database images: the sort keys of an image's queries span all of its tiles
+    size_t run_pos = 0;
+    for (int64_t u0 = 0; u0 < nunits;) {
+        int64_t u1 = u0;
+        while (run_pos < run.size() && (u1 == u0 || (int64_t) run[run_pos].unit0 + run[run_pos].nunits - u0 <= chunk_units)) {
+            u1 = (int64_t) run[run_pos].unit0 + run[run_pos].nunits;
+            run_pos++;
+        }
         P.unit_begin = (int32_t) u0; P.unit_end = (int32_t) u1;
         BSFM_CUDA_TRY(cudaMemsetAsync(P.counters, 0, 64, db->stream));
         BSFM_CUDA_TRY(cudaEventRecord(db->ev[1], db->stream));
@@ -286,11 +321,12 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
             count_launch(3);
             BSFM_CUDA_TRY(cudaGetLastError());
             match_finalize_kernel<<<(nmatch + 255) / 256, 256, 0, db->stream>>>((const uint32_t *) (S + o_slot_b), (const int32_t *) (S + o_idx_b),
-                                                                                nmatch, d_run, K, (int) u0, db->d_tile_img, db->d_img_doff,
+                                                                                nmatch, d_run, K, (int) u0, db->d_tile_img, db->d_img_doff, db->d_perm,
                                                                                 db->d_matches + 2 * db->total_matches, db->d_pair_counts);
             BSFM_KERNEL_CHECK();
             db->total_matches += nmatch;
         }
+        u0 = u1;
     }
     BSFM_CUDA_TRY(cudaEventRecord(db->ev[3], db->stream));
     BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
@@ -323,7 +359,7 @@ bsfm_keydb *bsfm_keydb_create_dev(const uint8_t *keys_dev, const int64_t *key_of
 void bsfm_keydb_destroy(bsfm_keydb *db)
 {
     if (!db) return;
-    cudaFree(db->d_keys_sw); cudaFree(db->d_norms); cudaFree(db->d_tile_img); cudaFree(db->d_img_doff);
+    cudaFree(db->d_keys_sw); cudaFree(db->d_norms); cudaFree(db->d_perm); cudaFree(db->d_tile_img); cudaFree(db->d_img_doff);
     cudaFree(db->d_pair_counts); cudaFree(db->d_matches); cudaFree(db->scratch);
     for (int e = 0; e < 4; e++) if (db->ev[e]) cudaEventDestroy(db->ev[e]);
     if (db->stream) cudaStreamDestroy(db->stream);

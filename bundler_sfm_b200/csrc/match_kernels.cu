@@ -6,35 +6,49 @@ namespace bsfm {
 namespace match {
 
 // ---------------------------------------------------------------------------------------------
-// prep: raw host-order descriptors (n_i x 128 per image, concatenated) -> padded swizzled layout
-// + squared norms.  One warp per device row; lane l handles bytes [4l, 4l+4).
+// prep: raw host-order descriptors (n_i x 128 per image, concatenated) -> squared norms (for the per-image
+// sort), then the padded, norm-sorted, swizzled layout.  One warp per row; lane l handles bytes [4l, 4l+4).
 // ---------------------------------------------------------------------------------------------
+__global__ void raw_norm_kernel(const uint8_t *__restrict__ raw, int64_t total_keys, int32_t *__restrict__ norms_raw, int32_t *__restrict__ iota)
+{
+    const int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= total_keys) return;
+    const uint8_t *src = raw + row * DESC_BYTES + lane * 4;
+    const uint32_t w = (uint32_t) src[0] | ((uint32_t) src[1] << 8) | ((uint32_t) src[2] << 16) | ((uint32_t) src[3] << 24);
+    uint32_t s = __dp4a(w, w, 0u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { norms_raw[row] = (int32_t) s; iota[row] = (int32_t) row; }
+}
+
+// sorted_src[key_off[img] + pos] = raw row (global) that is the pos-th smallest-norm key of image img
 __global__ void prep_kernel(const uint8_t *__restrict__ raw, const int64_t *__restrict__ key_off,
                             const int32_t *__restrict__ img_doff, const int32_t *__restrict__ tile_img,
-                            uint8_t *__restrict__ keys_sw, int32_t *__restrict__ norms, int64_t drows)
+                            const int32_t *__restrict__ sorted_src, const int32_t *__restrict__ sorted_norms,
+                            uint8_t *__restrict__ keys_sw, int32_t *__restrict__ norms, int32_t *__restrict__ perm, int64_t drows)
 {
     int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= drows) return;
     int img = tile_img[row >> 7];
     uint32_t w = 0;
-    int32_t nrm = NORM_PAD;
+    int32_t nrm = NORM_PAD, orig = -1;
     if (img >= 0) {
         int64_t k = row - img_doff[img];
         int64_t n = key_off[img + 1] - key_off[img];
         if (k < n) {
-            const uint8_t *src = raw + (key_off[img] + k) * DESC_BYTES + lane * 4;
+            const int64_t srow = sorted_src[key_off[img] + k];
+            const uint8_t *src = raw + srow * DESC_BYTES + lane * 4;
             w = (uint32_t) src[0] | ((uint32_t) src[1] << 8) | ((uint32_t) src[2] << 16) | ((uint32_t) src[3] << 24);
-            uint32_t s = __dp4a(w, w, 0u);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            nrm = (int32_t) s;
+            nrm = sorted_norms[key_off[img] + k];
+            orig = (int32_t) (srow - key_off[img]);
         }
     }
     int c = lane >> 2;  // 16-byte chunk
     uint32_t *dst = reinterpret_cast<uint32_t *>(keys_sw + sw_chunk_offset(row, c)) + (lane & 3);
     *dst = w;
-    if (lane == 0) norms[row] = nrm;
+    if (lane == 0) { norms[row] = nrm; perm[row] = orig; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(256) match_dp4a_kernel(MatchParams P)
             if ((double) d0 < P.ratio_sq * (double) d1) {
                 int pos = atomicAdd(&P.counters[1], 1);
                 if (pos < P.match_cap) {
-                    P.match_slot[pos] = (uint32_t) (u - P.unit_begin) * TILE_Q + r;
+                    P.match_slot[pos] = match_sort_key(P, R, a_row0 + r);
                     P.match_idx2[pos] = mi[a];
                 } else {
                     P.counters[2] = 1;
@@ -560,7 +574,9 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
         if ((double) d0 < P.ratio_sq * (double) d1) {
             int pos = atomicAdd(&P.counters[1], 1);
             if (pos < P.match_cap) {
-                P.match_slot[pos] = (uint32_t) slot;
+                const int u = P.unit_begin + (slot >> 7);
+                const RunImage R = P.run_imgs[find_run_image(P.run_imgs, P.num_run_imgs, u)];
+                P.match_slot[pos] = match_sort_key(P, R, qrow);
                 P.match_idx2[pos] = col0 + mi;
             } else {
                 P.counters[2] = 1;
@@ -575,6 +591,7 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
 __global__ void match_finalize_kernel(const uint32_t *__restrict__ slots, const int32_t *__restrict__ idx2,
                                       int nmatch, const RunImage *__restrict__ run_imgs, int K, int unit_begin,
                                       const int32_t *__restrict__ tile_img, const int32_t *__restrict__ img_doff,
+                                      const int32_t *__restrict__ perm,
                                       int32_t *__restrict__ out_pairs /* [nmatch][2] */,
                                       int32_t *__restrict__ pair_counts)
 {
@@ -589,7 +606,7 @@ __global__ void match_finalize_kernel(const uint32_t *__restrict__ slots, const 
     const int j = tile_img[atile];
     const int idx1 = atile * TILE_Q + r - img_doff[j];
     out_pairs[2 * (size_t) e + 0] = idx1;
-    out_pairs[2 * (size_t) e + 1] = idx2[e];
+    out_pairs[2 * (size_t) e + 1] = perm[(size_t) R.db_row0 + idx2[e]];   // norm-sorted position -> caller's key index
     atomicAdd(&pair_counts[R.pair0 + (j - R.start_img)], 1);
 }
 

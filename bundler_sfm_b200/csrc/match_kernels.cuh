@@ -6,7 +6,8 @@
 //     (d0, nn0), d1 = two smallest over p in image i lib/ann_1.1_char/src/pr_queue_k.h:102-117
 //     emit (q, nn0) iff (double)d0 < ratio*ratio*(double)d1        src/keys2a.cpp:362
 //
-// HBM layout: every image is padded to a multiple of 256 descriptor rows; a row is
+// HBM layout: inside every image the keys are stored in ascending order of their squared norm
+// (perm[] maps a device row back to the caller's index); every image is padded to a multiple of 256 descriptor rows; a row is
 // 128 bytes; rows are stored in the UMMA "K-major, SWIZZLE_128B" canonical shared-memory image
 // (8-row x 128-byte atoms, 16-byte chunk c of row r stored at chunk c ^ (r & 7)) so that a tile
 // of rows is ONE contiguous TMA bulk copy and lands in shared memory ready for tcgen05.mma.
@@ -65,7 +66,10 @@ struct RunImage {
 
 struct MatchParams {
     const uint8_t *keys_sw;     // swizzled padded descriptors
-    const int32_t *norms;       // per device row
+    const int32_t *norms;       // per device row (ascending inside every image)
+    const int32_t *perm;        // per device row: index of the key in the caller's order (-1 for padding)
+    const int32_t *tile_img;    // image of every 128-row tile
+    const int32_t *img_doff;    // first device row of every image
     const RunImage *run_imgs;   // K entries, unit0 ascending
     int32_t num_run_imgs;
     int32_t unit_begin;         // units [unit_begin, unit_end) are processed by this launch
@@ -86,6 +90,17 @@ struct MatchParams {
 __host__ __device__ __forceinline__ size_t sw_chunk_offset(int64_t row, int c)
 {
     return (size_t) (row >> 3) * 1024 + (size_t) (row & 7) * 128 + (size_t) ((c ^ (int) (row & 7)) << 4);
+}
+
+// Sort key of a match: queries of image j occupy the slot range that starts at the first tile of j for this
+// database image; the key is that base plus the query's index in the CALLER's order, so sorting by key restores
+// KeyMatchFull's order (i ascending, j ascending, query ascending) although rows are stored norm-sorted.
+__device__ __forceinline__ uint32_t match_sort_key(const MatchParams &P, const RunImage &R, int64_t qrow)
+{
+    const int atile = (int) (qrow >> 7);
+    const int j = P.tile_img[atile];
+    const int base_unit = R.unit0 + (P.img_doff[j] >> 7) - R.atile0;
+    return (uint32_t) (base_unit - P.unit_begin) * TILE_Q + (uint32_t) P.perm[qrow];
 }
 
 // find the run image that owns work unit u (binary search over unit0)

@@ -18,7 +18,9 @@ __global__ void raw_norm_kernel(const uint8_t *, int64_t, int32_t *, int32_t *);
 __global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, const int32_t *, const int32_t *, const int32_t *, uint8_t *, int32_t *, int32_t *, int64_t);
 __global__ void match_dp4a_kernel(MatchParams);
 __global__ void match_tc_kernel(MatchParams);
+__global__ void match_tc_bound_kernel(MatchParams);
 __global__ void match_verify_kernel(MatchParams, int);
+__global__ void match_fullscan_kernel(MatchParams, int);
 __global__ void match_finalize_kernel(const uint32_t *, const int32_t *, int, const RunImage *, int, int,
                                       const int32_t *, const int32_t *, const int32_t *, int32_t *, int32_t *);
 }  // namespace match
@@ -50,6 +52,7 @@ struct bsfm_keydb {
     int64_t match_cap = 0;
     float ms[3] = {0, 0, 0};
     int launches = 0;
+    int64_t cand_rows = 0, hard_rows = 0;   // statistics of the last run (tensor-core kernel)
     // scratch reused across runs
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -208,6 +211,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     }
     db->shard_pairs = npairs;
     db->total_matches = 0;
+    db->cand_rows = db->hard_rows = 0;
     db->ms[0] = db->ms[1] = db->ms[2] = 0;
 
     if (npairs > db->pair_cap) {
@@ -243,7 +247,8 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
                                     (const int32_t *) nullptr, (int32_t *) nullptr, (int) std::min<int64_t>(cap, INT_MAX), 0, 32, db->stream);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t) 255; return o; };
-    const size_t o_cand = carve((size_t) cap * 6 * sizeof(int32_t));
+    const size_t o_cand = carve((size_t) cap * 7 * sizeof(int32_t));
+    const size_t o_hard = carve((size_t) cap * 2 * sizeof(int32_t));
     const size_t o_slot_a = carve((size_t) cap * sizeof(uint32_t));
     const size_t o_slot_b = carve((size_t) cap * sizeof(uint32_t));
     const size_t o_idx_a = carve((size_t) cap * sizeof(int32_t));
@@ -260,12 +265,18 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     P.ratio_sq = ratio * ratio;
     P.neg2 = -2;
     P.cand = (int32_t *) (S + o_cand); P.cand_cap = (int32_t) cap;
+    P.hard = (int32_t *) (S + o_hard);
+    // 1 = bound epilogue (default; needs every image to fit the kernel's norm staging buffer), 0 = exact chunk minima
+    int32_t max_img_rows = 0;
+    for (int i = 0; i < db->N; i++) max_img_rows = std::max(max_img_rows, db->doff[i + 1] - db->doff[i]);
+    P.epi_mode = (env_int("BSFM_MATCH_EPILOGUE", 1) == 1 && max_img_rows <= TC_NORM_CAP) ? 1 : 0;
     P.match_slot = (uint32_t *) (S + o_slot_a); P.match_idx2 = (int32_t *) (S + o_idx_a); P.match_cap = (int32_t) cap;
     P.counters = (int32_t *) (S + o_cnt);
 
     static bool attr_set = false;
     if (!attr_set) {
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
+        BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         attr_set = true;
     }
 
@@ -288,7 +299,8 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
         } else {
             const int grid = (int) std::min<int64_t>(db->num_sms, u1 - u0);
-            match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
+            if (P.epi_mode == 1) match_tc_bound_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
+            else match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
             BSFM_KERNEL_CHECK();
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
             BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
@@ -299,6 +311,15 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
                 const int64_t threads = (int64_t) ncand * 32;
                 match_verify_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, db->stream>>>(P, ncand);
                 BSFM_KERNEL_CHECK();
+                BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
+                BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+                if (h_cnt[2]) { set_error("bsfm_match_run: hard-row buffer overflow (internal)"); cudaFree(d_run); return BSFM_ERR_CUDA; }
+                const int nhard = h_cnt[3];
+                db->hard_rows += nhard; db->cand_rows += ncand;
+                if (nhard > 0) {
+                    match_fullscan_kernel<<<(unsigned) (((int64_t) nhard * 32 + 255) / 256), 256, 0, db->stream>>>(P, nhard);
+                    BSFM_KERNEL_CHECK();
+                }
             }
         }
         BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
@@ -335,6 +356,9 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     cudaEventElapsedTime(&ms_total, db->ev[0], db->ev[3]);
     db->ms[0] = ms_search; db->ms[1] = ms_total - ms_search; db->ms[2] = ms_total;
     db->launches = (int) (g_kernel_launches.load() - launches0);
+    if (env_int("BSFM_MATCH_VERBOSE", 0))
+        fprintf(stderr, "[bsfm_match_run] candidates %lld, hard rows %lld, matches %lld\n", (long long) db->cand_rows,
+                (long long) db->hard_rows, (long long) db->total_matches);
     return db->total_matches;
 }
 

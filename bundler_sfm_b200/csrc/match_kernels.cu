@@ -299,7 +299,10 @@ __device__ __forceinline__ UnitInfo decode_unit(const MatchParams &P, int u)
     return U;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
+// BOUND = true : bound epilogue (every database image of the launch fits the norm staging buffer)
+// BOUND = false: exact chunk-minimum epilogue (any image size)
+template <bool BOUND>
+__device__ __forceinline__ void match_tc_body(const MatchParams &P)
 {
     extern __shared__ uint8_t smem_raw[];
     // manual 1024-byte alignment (SWIZZLE_128B atoms)
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
             mbar_init(bar_a_full + 8 * s, 1);
             mbar_init(bar_a_empty + 8 * s, 1);
             mbar_init(bar_t_full + 8 * s, 1);
-            mbar_init(bar_t_empty + 8 * s, TC_EPI_THREADS);
+            mbar_init(bar_t_empty + 8 * s, BOUND ? TC_EPI_THREADS / 2 : TC_EPI_THREADS);   // bound mode: one warp group per stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -399,24 +402,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
         const int row = quad * 32 + lane;        // query row inside the unit
         const int etid = threadIdx.x - 64;       // 0..TC_EPI_THREADS-1
         const int neg2 = P.neg2;                 // runtime -2: keeps the multiply-add on the FMA pipe (IMAD)
-        int *xch = reinterpret_cast<int *>(smem + TC_SMEM_XCH);   // [NPART-1][3][128] exchange between column parts
+        int *xch = reinterpret_cast<int *>(smem + TC_SMEM_XCH);   // [NPART-1][5][128] exchange between column parts
         int *sNall = reinterpret_cast<int *>(smem + TC_SMEM_NALL);
         int staged_row0 = -1;
         uint32_t ts = 0, tph = 0;
+        // bound mode: two warp groups, each owning one accumulator stage (see the tile loop)
+        constexpr int GNPART = NPART / 2;                 // column parts per tile inside a group
+        constexpr int GNCH = TILE_DB / CHUNK / (GNPART > 0 ? GNPART : 1);
+        const uint32_t grp = (uint32_t) part & 1u;        // accumulator stage / tile parity this warp serves
+        const int gpart = part >> 1;
+        uint32_t gtile = 0, gph = 0;                      // running tile number at unit start, phase of the group's stage
         for (int u = u_first; u < P.unit_end; u += u_step) {
             const UnitInfo U = decode_unit(P, u);
             const int na = P.norms[U.a_row0 + row];
-            int m1 = INT_MAX, s2 = INT_MAX, bchunk = 0;
+            // row state.  exact mode : m1 = smallest chunk-min of t, s2 = second smallest chunk-min, bchunk.
+            //             bound mode : m1 = smallest chunk LOWER bound, s2 = second smallest lower bound,
+            //                          ubb = UPPER bound of the best chunk, uo = smallest upper bound of the others.
+            int m1 = INT_MAX, s2 = INT_MAX, bchunk = 0, ubb = INT_MAX, uo = INT_MAX;
             // Database norms: when the whole image fits (<= TC_NORM_CAP rows) they are staged ONCE per
             // (CTA, database image) -- consecutive units of a CTA share the image -- so the tile loop has
             // no CTA-level barrier; larger images fall back to staging 256 norms per tile.
-            const bool whole = U.ntiles_db * TILE_DB <= TC_NORM_CAP;
+            const bool whole = BOUND ? true : (U.ntiles_db * TILE_DB <= TC_NORM_CAP);   // host guarantees it when BOUND
+            // bound mode (default): keys are norm-sorted inside an image, so a chunk's norms span
+            // [norm(first), norm(last)] and  min_c t  lies in  [nbmin - 2 vmax, nbmax - 2 vmax]  with vmax the
+            // chunk's largest dot product: the hot loop is a bare 3-input MAX tree (0.5 instruction / element).
+            constexpr bool bound = BOUND;   // host guarantees `whole` for every image when BOUND
             if (whole && staged_row0 != U.db_row0) {
                 asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // everyone done with the old image
                 for (int q = etid; q < U.ntiles_db * TILE_DB; q += TC_EPI_THREADS) sNall[q] = P.norms[(size_t) U.db_row0 + q];
                 asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
                 staged_row0 = U.db_row0;
             }
+            if constexpr (BOUND) {
+                // The epilogue warps form TWO groups; group g reduces the tiles whose running number is g (mod 2),
+                // i.e. it owns accumulator stage g.  The groups run half a tile period apart, so while one waits
+                // for its accumulator / its first TMEM load the other keeps the ALU pipe busy.  Inside a tile the
+                // TMEM loads are software pipelined (chunk c+1 in flight while chunk c is reduced) and the stage
+                // is handed back to the MMA warp as soon as its last chunk sits in registers.
+                static_assert(BCHUNK % CHUNK == 0 && (GNCH * CHUNK) % BCHUNK == 0, "bound chunk must tile a column part");
+                const uint32_t tlane = tmem_base + ((uint32_t) (quad * 32) << 16) + grp * TILE_DB + gpart * (TILE_DB / GNPART);
+                for (int t = (int) ((grp ^ gtile) & 1u); t < U.ntiles_db; t += 2) {
+                    const int *nbs = sNall + t * TILE_DB + gpart * (TILE_DB / GNPART);
+                    mbar_wait(bar_t_full + 8 * grp, gph);
+                    tc_fence_after();
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(tlane, va);
+                    int vmax = 0;
+#pragma unroll
+                    for (int c = 0; c < GNCH; c++) {
+                        uint32_t (&v)[32] = (c & 1) ? vb : va;
+                        uint32_t (&vn)[32] = (c & 1) ? va : vb;
+                        tmem_ld_wait_regs(v);
+                        if (c + 1 < GNCH) {
+                            tmem_ld32(tlane + (c + 1) * CHUNK, vn);
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(bar_t_empty + 8 * grp);     // accumulator stage free again
+                            gph ^= 1;
+                        }
+                        // 3-input MAX (VIMNMX3) over the 32 values: four independent chains
+                        int a0 = max(max((int) v[0], (int) v[1]), vmax);
+                        int a1 = max(max((int) v[2], (int) v[3]), (int) v[4]);
+                        int a2 = max(max((int) v[5], (int) v[6]), (int) v[7]);
+                        int a3 = max(max((int) v[8], (int) v[9]), (int) v[10]);
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            a0 = max(max((int) v[11 + 8 * q], (int) v[12 + 8 * q]), a0);
+                            a1 = max(max((int) v[13 + 8 * q], (int) v[14 + 8 * q]), a1);
+                            a2 = max(max((int) v[15 + 8 * q], (int) v[16 + 8 * q]), a2);
+                            a3 = max(max((int) v[17 + 8 * q], (int) v[18 + 8 * q]), a3);
+                        }
+                        a0 = max(max((int) v[27], (int) v[28]), a0);
+                        a1 = max(max((int) v[29], (int) v[30]), a1);
+                        a2 = max((int) v[31], a2);
+                        vmax = max(max(a0, a1), max(a2, a3));
+                        if (((c + 1) * CHUNK) % BCHUNK == 0) {
+                            const int cb = ((c + 1) * CHUNK) / BCHUNK - 1;      // bound chunk inside this part
+                            const int chunk_id = t * (TILE_DB / BCHUNK) + gpart * (GNCH * CHUNK / BCHUNK) + cb;
+                            const int lb = vmax * neg2 + nbs[cb * BCHUNK];
+                            const int ub = vmax * neg2 + nbs[cb * BCHUNK + BCHUNK - 1];
+                            const bool nb_best = lb < m1;
+                            s2 = nb_best ? m1 : min(s2, lb);
+                            uo = min(uo, nb_best ? ubb : ub);
+                            ubb = nb_best ? ub : ubb;
+                            bchunk = nb_best ? chunk_id : bchunk;
+                            m1 = min(m1, lb);
+                            vmax = 0;
+                        }
+                    }
+                }
+                gtile += (uint32_t) U.ntiles_db;
+            } else {
             int nrm_next = (!whole && etid < TILE_DB) ? P.norms[(size_t) U.db_row0 + etid] : 0;
             for (int t = 0; t < U.ntiles_db; t++) {
                 const int4 *nb4;
@@ -443,6 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                     uint32_t (&vn)[32] = (c & 1) ? va : vb;
                     tmem_ld_wait_regs(v);
                     if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * CHUNK, vn);
+                    const int chunk_id = t * (TILE_DB / CHUNK) + part * NCH + c;
                     int cm = INT_MAX;
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
@@ -459,7 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                     }
                     // (m1, s2) <- two smallest of {m1, s2, cm}
                     const int hi = max(m1, cm);
-                    if (cm < m1) bchunk = t * (TILE_DB / CHUNK) + part * NCH + c;
+                    if (cm < m1) bchunk = chunk_id;
                     m1 = min(m1, cm);
                     s2 = min(s2, hi);
                 }
@@ -467,26 +544,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                 mbar_arrive(bar_t_empty + 8 * ts);
                 ts ^= 1; if (ts == 0) tph ^= 1;
             }
+            }
             // merge the column parts of every row (parts 1.. -> shared memory -> part 0)
-            if (part > 0) { int *x = xch + (part - 1) * 384; x[row] = m1; x[128 + row] = s2; x[256 + row] = bchunk; }
+            if (part > 0) { int *x = xch + (part - 1) * 640; x[row] = m1; x[128 + row] = s2; x[256 + row] = bchunk; x[384 + row] = ubb; x[512 + row] = uo; }
             asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");
             bool cand = false;
-            int d1u = INT_MAX;
+            int f5 = INT_MAX, f6 = INT_MAX;
             if (part == 0) {
 #pragma unroll
                 for (int pp = 0; pp < NPART - 1; pp++) {
-                    const int *x = xch + pp * 384;
-                    const int o1 = x[row], o2 = x[128 + row], ob = x[256 + row];
+                    const int *x = xch + pp * 640;
+                    const int o1 = x[row], o2 = x[128 + row], ob = x[256 + row], oub = x[384 + row], ouo = x[512 + row];
                     const int hi = max(m1, o1);
-                    if (o1 < m1) bchunk = ob;
+                    const bool other_wins = o1 < m1;
+                    uo = min(min(uo, ouo), other_wins ? ubb : oub);     // the loser's best chunk joins the "others"
+                    ubb = other_wins ? oub : ubb;
+                    if (other_wins) bchunk = ob;
                     m1 = min(m1, o1);
                     s2 = min(min(s2, o2), hi);
                 }
-                // unit finished: provisional ratio test with the upper bound on d1
                 if (na < NORM_PAD_HALF) {
-                    const int d0 = na + m1;
-                    d1u = (s2 >= NORM_PAD_HALF) ? INT_MAX : na + s2;
-                    cand = (double) d0 < P.ratio_sq * (double) d1u;
+                    if (bound) {
+                        // two distinct keys with t <= max(ubb, uo) exist, so d1 <= na + max(ubb, uo); d0 >= na + m1
+                        const int ubs = max(ubb, uo);
+                        const int d1u = (ubs >= NORM_PAD_HALF) ? INT_MAX : na + ubs;
+                        cand = (double) (na + m1) < P.ratio_sq * (double) d1u;
+                        f5 = s2; f6 = uo;
+                    } else {
+                        // exact d0, upper bound on d1
+                        const int d0 = na + m1;
+                        const int d1u = (s2 >= NORM_PAD_HALF) ? INT_MAX : na + s2;
+                        cand = (double) d0 < P.ratio_sq * (double) d1u;
+                        f5 = d1u;
+                    }
                 }
             }
             asm volatile("bar.sync 3, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // xch may be overwritten by the next unit
@@ -498,14 +588,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
                 if (cand) {
                     const int pos = basepos + __popc(ball & ((1u << lane) - 1u));
                     if (pos < P.cand_cap) {
-                        const int col0 = bchunk * CHUNK;
+                        constexpr int CW = BOUND ? BCHUNK : CHUNK;   // width of the chunk the verify kernel recomputes
+                        const int col0 = bchunk * CW;
                         const size_t cap = (size_t) P.cand_cap;
                         P.cand[0 * cap + pos] = (u - P.unit_begin) * TILE_Q + row;
                         P.cand[1 * cap + pos] = (int32_t) (U.a_row0 + row);
                         P.cand[2 * cap + pos] = U.db_row0 + col0;
                         P.cand[3 * cap + pos] = col0;
-                        P.cand[4 * cap + pos] = min(CHUNK, U.n - col0);
-                        P.cand[5 * cap + pos] = d1u;
+                        P.cand[4 * cap + pos] = min(CW, U.n - col0);
+                        P.cand[5 * cap + pos] = f5;
+                        P.cand[6 * cap + pos] = bound ? f6 : INT_MIN;   // INT_MIN marks an exact-mode candidate
                     } else {
                         P.counters[2] = 1;
                     }
@@ -521,6 +613,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P) { match_tc_body<false>(P); }
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_bound_kernel(MatchParams P) { match_tc_body<true>(P); }
 
 // ---------------------------------------------------------------------------------------------
 // verify: one warp per candidate.  Recomputes the 32 distances of the winning chunk with the
@@ -551,12 +646,16 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
     const int db0 = P.cand[2 * cap + w];
     const int col0 = P.cand[3 * cap + w];
     const int nvalid = P.cand[4 * cap + w];
-    const int d1u = P.cand[5 * cap + w];
+    const int f5 = P.cand[5 * cap + w];
+    const int f6 = P.cand[6 * cap + w];
 
-    int d = INT_MAX;
-    if (lane < nvalid) d = sqdist_rows(P.keys_sw, qrow, (int64_t) db0 + lane);
-    // warp top-2 (value, lane)
-    int m1 = d, m2 = INT_MAX, mi = lane;
+    // up to 64 rows per candidate (bound chunks may be 64 wide): two distances per lane, lane-local top-2 first
+    int m1 = INT_MAX, m2 = INT_MAX, mi = lane;
+    if (lane < nvalid) m1 = sqdist_rows(P.keys_sw, qrow, (int64_t) db0 + lane);
+    if (lane + 32 < nvalid) {
+        const int d = sqdist_rows(P.keys_sw, qrow, (int64_t) db0 + lane + 32);
+        if (d < m1) { m2 = m1; m1 = d; mi = lane + 32; } else m2 = d;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         int o1 = __shfl_xor_sync(0xffffffffu, m1, o);
@@ -569,9 +668,30 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
         m2 = min(hi, lo2);
     }
     if (lane == 0) {
-        const int d0 = m1;
-        const int d1 = min(d1u, m2);
-        if ((double) d0 < P.ratio_sq * (double) d1) {
+        bool match = false, hard = false;
+        if (f6 == INT_MIN) {
+            // exact mode: d0 = m1 is the global minimum, f5 bounds d1 from above through the other chunks
+            const int d1 = min(f5, m2);
+            match = (double) m1 < P.ratio_sq * (double) d1;
+        } else {
+            // bound mode: the chunk with the smallest lower bound was recomputed exactly (m1, m2).  It holds the
+            // global minimum iff m1 <= every other chunk's lower bound; d1 lies in [min(m2, L2), min(m2, Uo)].
+            const int na = P.norms[qrow];
+            const int l2d = (f5 >= NORM_PAD_HALF) ? INT_MAX : na + f5;
+            const int uod = (f6 >= NORM_PAD_HALF) ? INT_MAX : na + f6;
+            if (m1 > l2d) hard = true;
+            else {
+                const int d1_low = min(m2, l2d), d1_up = min(m2, uod);
+                if ((double) m1 < P.ratio_sq * (double) d1_low) match = true;
+                else if ((double) m1 < P.ratio_sq * (double) d1_up) hard = true;   // undecided inside the bound slack
+            }
+        }
+        if (hard) {
+            int pos = atomicAdd(&P.counters[3], 1);
+            if (pos < P.cand_cap) { P.hard[pos] = slot; P.hard[(size_t) P.cand_cap + pos] = qrow; }
+            else P.counters[2] = 1;
+        }
+        if (match) {
             int pos = atomicAdd(&P.counters[1], 1);
             if (pos < P.match_cap) {
                 const int u = P.unit_begin + (slot >> 7);
@@ -582,6 +702,42 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
                 P.counters[2] = 1;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// full scan: one warp per "hard" row (bounds undecided): exact two nearest keys over the whole database
+// image with the definition, final ratio test.  Rare by construction.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) match_fullscan_kernel(MatchParams P, int nhard)
+{
+    const int w = (int) (((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nhard) return;
+    const int slot = P.hard[w];
+    const int qrow = P.hard[(size_t) P.cand_cap + w];
+    const int u = P.unit_begin + (slot >> 7);
+    const RunImage R = P.run_imgs[find_run_image(P.run_imgs, P.num_run_imgs, u)];
+    int m1 = INT_MAX, m2 = INT_MAX, mi = -1;
+    for (int c = lane; c < R.n; c += 32) {
+        const int d = sqdist_rows(P.keys_sw, qrow, (int64_t) R.db_row0 + c);
+        if (d < m1) { m2 = m1; m1 = d; mi = c; } else if (d < m2) m2 = d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int o1 = __shfl_xor_sync(0xffffffffu, m1, o);
+        int o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        int hi = max(m1, o1);
+        int lo2 = min(m2, o2);
+        if (o1 < m1 || (o1 == m1 && oi >= 0 && (mi < 0 || oi < mi))) mi = oi;
+        m1 = min(m1, o1);
+        m2 = min(hi, lo2);
+    }
+    if (lane == 0 && (double) m1 < P.ratio_sq * (double) m2) {
+        int pos = atomicAdd(&P.counters[1], 1);
+        if (pos < P.match_cap) { P.match_slot[pos] = match_sort_key(P, R, qrow); P.match_idx2[pos] = mi; }
+        else P.counters[2] = 1;
     }
 }
 

@@ -45,7 +45,11 @@ constexpr int TC_SMEM_B = 2 * TC_A_BYTES;
 constexpr int TC_SMEM_N = TC_SMEM_B + TC_B_STAGES * TC_B_BYTES;   // 2 x 256 int32 norms
 constexpr int TC_SMEM_XCH = TC_SMEM_N + 2 * TILE_DB * 4;              // 3 x 128 int32 half-merge exchange
 constexpr int TC_NORM_CAP = 8192;                                      // norms of a whole database image kept in smem
-constexpr int TC_SMEM_NALL = TC_SMEM_XCH + 3 * 3 * 128 * 4;
+#ifndef BSFM_TC_BOUND_CHUNK
+#define BSFM_TC_BOUND_CHUNK 64
+#endif
+constexpr int BCHUNK = BSFM_TC_BOUND_CHUNK;   // columns per bound-epilogue chunk (32 or 64): width the verify kernel recomputes
+constexpr int TC_SMEM_NALL = TC_SMEM_XCH + 3 * 5 * 128 * 4;
 constexpr int TC_SMEM_BAR = TC_SMEM_NALL + TC_NORM_CAP * 4;
 constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
 constexpr int TC_SMEM_ALLOC = TC_SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
@@ -76,14 +80,17 @@ struct MatchParams {
     int32_t unit_end;
     double ratio_sq;            // ratio*ratio evaluated on the host in double (keys2a.cpp:362)
     int32_t neg2;               // the constant -2 as a runtime value (see the epilogue of match_tc_kernel)
-    // candidate list (tensor-core kernel): SoA int32 [6][cand_cap]: slot, qrow, db0, col0, nvalid, d1u
+    int32_t epi_mode;           // 1 = bound epilogue (max tree on norm-sorted chunks), 0 = exact chunk minima
+    // candidate list (tensor-core kernel): SoA int32 [7][cand_cap]: slot, qrow, db0, col0, nvalid, f5, f6
+    //   exact mode: f5 = upper bound on d1, f6 = INT_MIN;  bound mode: f5 = L2, f6 = Uo (t-space bounds of the other chunks)
     int32_t *cand;
+    int32_t *hard;              // [2][cand_cap]: slot, qrow of rows the bounds could not decide
     int32_t cand_cap;
     // match list (unordered): slot keys + idx2 values
     uint32_t *match_slot;
     int32_t *match_idx2;
     int32_t match_cap;
-    int32_t *counters;          // [0] = #candidates, [1] = #matches, [2] = overflow flag, [3] = d0 mismatches
+    int32_t *counters;          // [0] = #candidates, [1] = #matches, [2] = overflow flag, [3] = #hard rows
 };
 
 // byte offset of 16-byte chunk c (0..7) of device row r in the swizzled layout

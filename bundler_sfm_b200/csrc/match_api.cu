@@ -19,6 +19,7 @@ __global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, c
 __global__ void match_dp4a_kernel(MatchParams);
 __global__ void match_tc_kernel(MatchParams);
 __global__ void match_tc_bound_kernel(MatchParams);
+__global__ void match_tc_pair_kernel(MatchParams);
 __global__ void match_verify_kernel(MatchParams, int);
 __global__ void match_fullscan_kernel(MatchParams, int);
 __global__ void match_finalize_kernel(const uint32_t *, const int32_t *, int, const RunImage *, int, int,
@@ -270,6 +271,9 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     int32_t max_img_rows = 0;
     for (int i = 0; i < db->N; i++) max_img_rows = std::max(max_img_rows, db->doff[i + 1] - db->doff[i]);
     P.epi_mode = (env_int("BSFM_MATCH_EPILOGUE", 1) == 1 && max_img_rows <= TC_NORM_CAP) ? 1 : 0;
+    // cta_group::2 kernel (CTA pairs, half the L2 -> SM traffic) vs one CTA per unit (default: measured faster, the
+    // path is bound by the TMEM -> register read of the epilogue, not by L2)
+    const bool pair_mode = env_int("BSFM_MATCH_PAIR", 0) != 0;
     P.match_slot = (uint32_t *) (S + o_slot_a); P.match_idx2 = (int32_t *) (S + o_idx_a); P.match_cap = (int32_t) cap;
     P.counters = (int32_t *) (S + o_cnt);
 
@@ -277,6 +281,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     if (!attr_set) {
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
+        BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         attr_set = true;
     }
 
@@ -299,7 +304,19 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
         } else {
             const int grid = (int) std::min<int64_t>(db->num_sms, u1 - u0);
-            if (P.epi_mode == 1) match_tc_bound_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
+            if (P.epi_mode == 1 && pair_mode && (u1 - u0) % 2 == 0) {
+                // CTA pairs (cluster of 2 = one SM pair): one cta_group::2 MMA per database tile, each CTA stages half of it
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned) (2 * std::min<int64_t>(db->num_sms / 2, (u1 - u0) / 2)));
+                cfg.blockDim = dim3(TC_THREADS);
+                cfg.dynamicSmemBytes = TC_SMEM_ALLOC;
+                cfg.stream = db->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                BSFM_CUDA_TRY(cudaLaunchKernelEx(&cfg, match_tc_pair_kernel, P));
+            } else if (P.epi_mode == 1) match_tc_bound_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
             else match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
             BSFM_KERNEL_CHECK();
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));

@@ -257,6 +257,62 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
 // UINT8(0) [7,10)/[10,13), a/b K-major(0) [15],[16], N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t) (TILE_DB >> 3) << 17) | ((uint32_t) (TILE_Q >> 4) << 24);
 
+
+// ---- CTA-pair (cta_group::2) helpers --------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (own CTA allowed)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar), "r"(cta) : "memory");
+}
+// wait with cluster-scope acquire (the arrivals may come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_backoff_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
+}
+// commit of a cta_group::2 MMA: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t) 3) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows per CTA] * B[128 rows per CTA]^T : M = 256, N = 256 across the CTA pair
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t TC_IDESC_PAIR = (2u << 4) | ((uint32_t) (TILE_DB >> 3) << 17) | ((uint32_t) ((2 * TILE_Q) >> 4) << 24);
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -283,6 +339,17 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32])
                  :: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_wait_regs2(uint32_t (&v)[32], uint32_t (&w)[32])
+{
+    tmem_ld_wait_regs(v);
+    asm volatile(""
+                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
+                   "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]),
+                   "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]),
+                   "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
+                 :: "memory");
+}
+
 struct UnitInfo {
     int64_t a_row0;
     int32_t db_row0, n, ntiles_db;
@@ -301,7 +368,13 @@ __device__ __forceinline__ UnitInfo decode_unit(const MatchParams &P, int u)
 
 // BOUND = true : bound epilogue (every database image of the launch fits the norm staging buffer)
 // BOUND = false: exact chunk-minimum epilogue (any image size)
-template <bool BOUND>
+#ifndef BSFM_TC_MMA_SPIN
+#define BSFM_TC_MMA_SPIN 1
+#endif
+// PAIR  = true : two CTAs of a cluster (an SM pair) issue ONE cta_group::2 MMA per database tile: M = 256 (128
+//                query rows per CTA), every CTA stages only HALF of the 256-row database tile, which halves the
+//                L2 -> SM traffic per MAC (the single-CTA kernel is L2-bandwidth bound, profiles/r1_match_tc_v6).
+template <bool BOUND, bool PAIR>
 __device__ __forceinline__ void match_tc_body(const MatchParams &P)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -315,38 +388,54 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
     int32_t *sN = reinterpret_cast<int32_t *>(smem + TC_SMEM_N);
     const uint32_t bar0 = base + TC_SMEM_BAR;
     // barrier map (8 bytes each)
-    const uint32_t bar_b_full = bar0;                          // [TC_B_STAGES]
-    const uint32_t bar_b_empty = bar0 + 8 * TC_B_STAGES;       // [TC_B_STAGES]
-    const uint32_t bar_a_full = bar0 + 16 * TC_B_STAGES;       // [2]
+    constexpr int BST = PAIR ? 2 * TC_B_STAGES : TC_B_STAGES;       // database tile stages
+    constexpr uint32_t BSLOT = PAIR ? TC_B_BYTES / 2 : TC_B_BYTES;   // bytes this CTA stages per database tile
+    const uint32_t bar_b_full = bar0;                          // [BST]
+    const uint32_t bar_b_empty = bar0 + 8 * BST;               // [BST]
+    const uint32_t bar_a_full = bar0 + 16 * BST;               // [2]
     const uint32_t bar_a_empty = bar_a_full + 16;              // [2]
     const uint32_t bar_t_full = bar_a_empty + 16;              // [2]
     const uint32_t bar_t_empty = bar_t_full + 16;              // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_SMEM_BAR + 8 * (2 * TC_B_STAGES + 8));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_SMEM_BAR + 8 * (2 * BST + 8));
+    static_assert(8 * (2 * BST + 8) + 4 <= 256, "barrier region");
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_B_STAGES; s++) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+        // pair mode: the leader's "full" barriers also count the peer's relay arrival (its half is staged), and
+        // the leader's accumulator-empty barriers count one arrival per epilogue warp of the group in BOTH CTAs
+        const uint32_t full_cnt = (PAIR && crank == 0) ? 2 : 1;
+        for (int s = 0; s < BST; s++) { mbar_init(bar_b_full + 8 * s, full_cnt); mbar_init(bar_b_empty + 8 * s, 1); }
         for (int s = 0; s < 2; s++) {
-            mbar_init(bar_a_full + 8 * s, 1);
+            mbar_init(bar_a_full + 8 * s, full_cnt);
             mbar_init(bar_a_empty + 8 * s, 1);
             mbar_init(bar_t_full + 8 * s, 1);
-            mbar_init(bar_t_empty + 8 * s, BOUND ? TC_EPI_THREADS / 2 : TC_EPI_THREADS);   // bound mode: one warp group per stage
+            // bound mode: one warp group per stage; pair: one arrival per warp of the group in both CTAs
+            mbar_init(bar_t_empty + 8 * s, PAIR ? TC_EPI_WARPS : (BOUND ? TC_EPI_THREADS / 2 : TC_EPI_THREADS));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int u_first = P.unit_begin + blockIdx.x;
-    const int u_step = gridDim.x;
+    // pair mode: cluster c takes the unit pairs (2c, 2c+1), (2c + 2C, ...): both units share the database image
+    // (images are padded to 256 rows, so every image contributes an even number of 128-row query units)
+    const int u_first = PAIR ? P.unit_begin + 2 * (int) (blockIdx.x >> 1) + (int) crank : P.unit_begin + (int) blockIdx.x;
+    const int u_step = PAIR ? (int) (gridDim.x & ~1u) : (int) gridDim.x;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -358,12 +447,13 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                 mbar_expect_tx(bar_a_full + 8 * as, TC_A_BYTES);
                 tma_bulk_g2s(sA + as * TC_A_BYTES, P.keys_sw + (size_t) U.a_row0 * DESC_BYTES, TC_A_BYTES, bar_a_full + 8 * as);
                 as ^= 1; if (as == 0) aph ^= 1;
-                const uint8_t *src = P.keys_sw + (size_t) U.db_row0 * DESC_BYTES;
+                // pair mode: this CTA stages rows [128 crank, 128 crank + 128) of every 256-row database tile
+                const uint8_t *src = P.keys_sw + (size_t) U.db_row0 * DESC_BYTES + (PAIR ? crank * BSLOT : 0u);
                 for (int t = 0; t < U.ntiles_db; t++) {
                     mbar_wait_backoff(bar_b_empty + 8 * bs, bph ^ 1);
-                    mbar_expect_tx(bar_b_full + 8 * bs, TC_B_BYTES);
-                    tma_bulk_g2s(sB + bs * TC_B_BYTES, src + (size_t) t * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * bs);
-                    if (++bs == TC_B_STAGES) { bs = 0; bph ^= 1; }
+                    mbar_expect_tx(bar_b_full + 8 * bs, BSLOT);
+                    tma_bulk_g2s(sB + bs * BSLOT, src + (size_t) t * TC_B_BYTES, BSLOT, bar_b_full + 8 * bs);
+                    if (++bs == BST) { bs = 0; bph ^= 1; }
                 }
             }
         }
@@ -371,26 +461,49 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t bs = 0, bph = 0, as = 0, aph = 0, ts = 0, tph = 0;
+            if (PAIR && crank != 0) {
+                // peer CTA: no MMA to issue.  This warp relays "my half is staged" to the leader's barriers.
+                for (int u = u_first; u < P.unit_end; u += u_step) {
+                    const UnitInfo U = decode_unit(P, u);
+                    mbar_wait_backoff(bar_a_full + 8 * as, aph);
+                    mbar_arrive_cluster(bar_a_full + 8 * as, 0);
+                    as ^= 1; if (as == 0) aph ^= 1;
+                    for (int t = 0; t < U.ntiles_db; t++) {
+                        mbar_wait_backoff(bar_b_full + 8 * bs, bph);
+                        mbar_arrive_cluster(bar_b_full + 8 * bs, 0);
+                        if (++bs == BST) { bs = 0; bph ^= 1; }
+                    }
+                }
+            } else {
             for (int u = u_first; u < P.unit_end; u += u_step) {
                 const UnitInfo U = decode_unit(P, u);
-                mbar_wait_backoff(bar_a_full + 8 * as, aph);
+                if (PAIR) mbar_wait_backoff_cluster(bar_a_full + 8 * as, aph); else mbar_wait_backoff(bar_a_full + 8 * as, aph);
                 const uint64_t adesc = make_sw128_desc(sA + as * TC_A_BYTES);
                 for (int t = 0; t < U.ntiles_db; t++) {
-                    mbar_wait_backoff(bar_b_full + 8 * bs, bph);
-                    mbar_wait_backoff(bar_t_empty + 8 * ts, tph ^ 1);
+                    if (PAIR) {
+                        mbar_wait_backoff_cluster(bar_b_full + 8 * bs, bph);
+                        mbar_wait_backoff_cluster(bar_t_empty + 8 * ts, tph ^ 1);
+                    } else {
+                        mbar_wait_backoff(bar_b_full + 8 * bs, bph);
+                        // the accumulator-stage hand-over is on the critical path: poll without sleeping
+                        if (BSFM_TC_MMA_SPIN) mbar_wait(bar_t_empty + 8 * ts, tph ^ 1); else mbar_wait_backoff(bar_t_empty + 8 * ts, tph ^ 1);
+                    }
                     tc_fence_after();
-                    const uint64_t bdesc = make_sw128_desc(sB + bs * TC_B_BYTES);
+                    const uint64_t bdesc = make_sw128_desc(sB + bs * BSLOT);
                     const uint32_t tmem_d = tmem_base + ts * TILE_DB;
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++)   // K = 4 x 32 bytes; +32 B = +2 in the descriptor start field
-                        tc_mma_i8(tmem_d, adesc + (uint64_t) (kk * 2), bdesc + (uint64_t) (kk * 2), TC_IDESC, kk > 0);
-                    tc_commit(bar_b_empty + 8 * bs);
-                    tc_commit(bar_t_full + 8 * ts);
-                    if (++bs == TC_B_STAGES) { bs = 0; bph ^= 1; }
+                    for (int kk = 0; kk < 4; kk++) {  // K = 4 x 32 bytes; +32 B = +2 in the descriptor start field
+                        if (PAIR) tc_mma_i8_pair(tmem_d, adesc + (uint64_t) (kk * 2), bdesc + (uint64_t) (kk * 2), TC_IDESC_PAIR, kk > 0);
+                        else tc_mma_i8(tmem_d, adesc + (uint64_t) (kk * 2), bdesc + (uint64_t) (kk * 2), TC_IDESC, kk > 0);
+                    }
+                    if (PAIR) { tc_commit_pair(bar_b_empty + 8 * bs); tc_commit_pair(bar_t_full + 8 * ts); }
+                    else { tc_commit(bar_b_empty + 8 * bs); tc_commit(bar_t_full + 8 * ts); }
+                    if (++bs == BST) { bs = 0; bph ^= 1; }
                     ts ^= 1; if (ts == 0) tph ^= 1;
                 }
-                tc_commit(bar_a_empty + 8 * as);
+                if (PAIR) tc_commit_pair(bar_a_empty + 8 * as); else tc_commit(bar_a_empty + 8 * as);
                 as ^= 1; if (as == 0) aph ^= 1;
+            }
             }
         }
     } else {
@@ -457,7 +570,13 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                             tmem_ld32(tlane + (c + 1) * CHUNK, vn);
                         } else {
                             tc_fence_before();
-                            mbar_arrive(bar_t_empty + 8 * grp);     // accumulator stage free again
+                            if (PAIR) {
+                                // one arrival per warp on the LEADER's barrier (its MMA overwrites both CTAs' stage)
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(bar_t_empty + 8 * grp, 0);
+                            } else {
+                                mbar_arrive(bar_t_empty + 8 * grp);     // accumulator stage free again
+                            }
                             gph ^= 1;
                         }
                         // 3-input MAX (VIMNMX3) over the 32 values: four independent chains
@@ -608,14 +727,18 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // neither CTA may leave (or free tensor memory) while the pair's MMAs / remote arrives are in flight
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P) { match_tc_body<false>(P); }
-__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_bound_kernel(MatchParams P) { match_tc_body<true>(P); }
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P) { match_tc_body<false, false>(P); }
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_bound_kernel(MatchParams P) { match_tc_body<true, false>(P); }
+// launched with cluster dimension (2, 1, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_pair_kernel(MatchParams P) { match_tc_body<true, true>(P); }
 
 // ---------------------------------------------------------------------------------------------
 // verify: one warp per candidate.  Recomputes the 32 distances of the winning chunk with the

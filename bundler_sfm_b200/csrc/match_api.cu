@@ -303,7 +303,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
             BSFM_KERNEL_CHECK();
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
         } else {
-            const int grid = (int) std::min<int64_t>(db->num_sms, u1 - u0);
+            const int grid = (int) std::min<int64_t>(env_int("BSFM_MATCH_GRID", db->num_sms), u1 - u0);   // env: dev experiments only
             if (P.epi_mode == 1 && pair_mode && (u1 - u0) % 2 == 0) {
                 // CTA pairs (cluster of 2 = one SM pair): one cta_group::2 MMA per database tile, each CTA stages half of it
                 cudaLaunchConfig_t cfg = {};

@@ -339,35 +339,76 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32])
                  :: "memory");
 }
 
-__device__ __forceinline__ void tmem_ld_wait_regs2(uint32_t (&v)[32], uint32_t (&w)[32])
+// 3-input MAX (VIMNMX3) over the 32 values of a chunk and `init`: four independent chains
+__device__ __forceinline__ int chunk_max(const uint32_t (&v)[32], int init)
 {
-    tmem_ld_wait_regs(v);
-    asm volatile(""
-                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
-                   "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]),
-                   "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]),
-                   "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
-                 :: "memory");
+    int a0 = max(max((int) v[0], (int) v[1]), init);
+    int a1 = max(max((int) v[2], (int) v[3]), (int) v[4]);
+    int a2 = max(max((int) v[5], (int) v[6]), (int) v[7]);
+    int a3 = max(max((int) v[8], (int) v[9]), (int) v[10]);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        a0 = max(max((int) v[11 + 8 * q], (int) v[12 + 8 * q]), a0);
+        a1 = max(max((int) v[13 + 8 * q], (int) v[14 + 8 * q]), a1);
+        a2 = max(max((int) v[15 + 8 * q], (int) v[16 + 8 * q]), a2);
+        a3 = max(max((int) v[17 + 8 * q], (int) v[18 + 8 * q]), a3);
+    }
+    a0 = max(max((int) v[27], (int) v[28]), a0);
+    a1 = max(max((int) v[29], (int) v[30]), a1);
+    a2 = max((int) v[31], a2);
+    return max(max(a0, a1), max(a2, a3));
 }
 
 struct UnitInfo {
     int64_t a_row0;
     int32_t db_row0, n, ntiles_db;
 };
-__device__ __forceinline__ UnitInfo decode_unit(const MatchParams &P, int u)
+// Work units of a CTA ascend, and most consecutive units stay inside the same run image: every role keeps a cursor
+// (the image's unit range and fields in registers) and only touches global memory when a unit leaves the image --
+// a binary search per unit would put a chain of dependent global loads on the MMA thread's critical path.
+struct UnitCursor {
+    int32_t k = -1, unit0 = 0, unit_end = 0;      // current run image and its unit range [unit0, unit_end)
+    int32_t atile0 = 0, db_row0 = 0, n = 0, ntiles_db = 0;
+};
+__device__ __forceinline__ void cursor_load(const MatchParams &P, UnitCursor &c)
 {
-    const int k = find_run_image(P.run_imgs, P.num_run_imgs, u);
-    const RunImage *R = P.run_imgs + k;
+    const RunImage *R = P.run_imgs + c.k;
+    c.unit0 = R->unit0; c.unit_end = R->unit0 + R->nunits;
+    c.atile0 = R->atile0; c.db_row0 = R->db_row0; c.n = R->n; c.ntiles_db = R->ntiles_db;
+}
+__device__ __forceinline__ UnitInfo decode_unit(const MatchParams &P, UnitCursor &c, int u)
+{
+    if (c.k < 0 || u >= c.unit_end) {
+        if (c.k >= 0 && c.k + 1 < P.num_run_imgs) { c.k++; cursor_load(P, c); }       // usually the next image
+        if (c.k < 0 || u < c.unit0 || u >= c.unit_end) { c.k = find_run_image(P.run_imgs, P.num_run_imgs, u); cursor_load(P, c); }
+    }
     UnitInfo U;
-    U.a_row0 = (int64_t) (R->atile0 + (u - R->unit0)) * TILE_Q;
-    U.db_row0 = R->db_row0;
-    U.n = R->n;
-    U.ntiles_db = R->ntiles_db;
+    U.a_row0 = (int64_t) (c.atile0 + (u - c.unit0)) * TILE_Q;
+    U.db_row0 = c.db_row0;
+    U.n = c.n;
+    U.ntiles_db = c.ntiles_db;
     return U;
 }
 
 // BOUND = true : bound epilogue (every database image of the launch fits the norm staging buffer)
 // BOUND = false: exact chunk-minimum epilogue (any image size)
+// Dev-only cycle accounting of the pipeline roles (scripts/dev_match_prof.py builds a library with -DBSFM_TC_PROFILE):
+// g_prof[0..3] MMA thread: wait b_full, wait t_empty, issue, tiles;  [4..6] producer: wait b_empty, issue, tiles;
+// [8..11] epilogue warp 2 lane 0: wait t_full, loads+reduce until release, after release, tiles.  CTA 0 only.
+#ifdef BSFM_TC_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(i, v) do { if (blockIdx.x == 0) atomicAdd(&g_prof[i], (unsigned long long) (v)); } while (0)
+extern "C" int bsfm_debug_prof(unsigned long long *out)
+{
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out, g_prof, sizeof z) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(g_prof, z, sizeof z) == cudaSuccess ? 0 : -1;
+}
+#else
+#define PROF_T(var) do {} while (0)
+#define PROF_ADD(i, v) do {} while (0)
+#endif
 #ifndef BSFM_TC_MMA_SPIN
 #define BSFM_TC_MMA_SPIN 1
 #endif
@@ -413,7 +454,7 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
             mbar_init(bar_a_empty + 8 * s, 1);
             mbar_init(bar_t_full + 8 * s, 1);
             // bound mode: one warp group per stage; pair: one arrival per warp of the group in both CTAs
-            mbar_init(bar_t_empty + 8 * s, PAIR ? TC_EPI_WARPS : (BOUND ? TC_EPI_THREADS / 2 : TC_EPI_THREADS));
+            mbar_init(bar_t_empty + 8 * s, !BOUND ? TC_EPI_THREADS : (PAIR ? 2 : 1) * TC_EPI_WARPS / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -441,8 +482,9 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t bs = 0, bph = 0, as = 0, aph = 0;
+            UnitCursor cur;
             for (int u = u_first; u < P.unit_end; u += u_step) {
-                const UnitInfo U = decode_unit(P, u);
+                const UnitInfo U = decode_unit(P, cur, u);
                 mbar_wait_backoff(bar_a_empty + 8 * as, aph ^ 1);
                 mbar_expect_tx(bar_a_full + 8 * as, TC_A_BYTES);
                 tma_bulk_g2s(sA + as * TC_A_BYTES, P.keys_sw + (size_t) U.a_row0 * DESC_BYTES, TC_A_BYTES, bar_a_full + 8 * as);
@@ -450,10 +492,14 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                 // pair mode: this CTA stages rows [128 crank, 128 crank + 128) of every 256-row database tile
                 const uint8_t *src = P.keys_sw + (size_t) U.db_row0 * DESC_BYTES + (PAIR ? crank * BSLOT : 0u);
                 for (int t = 0; t < U.ntiles_db; t++) {
+                    PROF_T(p0);
                     mbar_wait_backoff(bar_b_empty + 8 * bs, bph ^ 1);
+                    PROF_T(p1);
                     mbar_expect_tx(bar_b_full + 8 * bs, BSLOT);
                     tma_bulk_g2s(sB + bs * BSLOT, src + (size_t) t * TC_B_BYTES, BSLOT, bar_b_full + 8 * bs);
                     if (++bs == BST) { bs = 0; bph ^= 1; }
+                    PROF_T(p2);
+                    PROF_ADD(4, p1 - p0); PROF_ADD(5, p2 - p1); PROF_ADD(6, 1);
                 }
             }
         }
@@ -463,8 +509,9 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
             uint32_t bs = 0, bph = 0, as = 0, aph = 0, ts = 0, tph = 0;
             if (PAIR && crank != 0) {
                 // peer CTA: no MMA to issue.  This warp relays "my half is staged" to the leader's barriers.
-                for (int u = u_first; u < P.unit_end; u += u_step) {
-                    const UnitInfo U = decode_unit(P, u);
+                UnitCursor cur;
+            for (int u = u_first; u < P.unit_end; u += u_step) {
+                    const UnitInfo U = decode_unit(P, cur, u);
                     mbar_wait_backoff(bar_a_full + 8 * as, aph);
                     mbar_arrive_cluster(bar_a_full + 8 * as, 0);
                     as ^= 1; if (as == 0) aph ^= 1;
@@ -475,19 +522,27 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                     }
                 }
             } else {
+            UnitCursor cur;
             for (int u = u_first; u < P.unit_end; u += u_step) {
-                const UnitInfo U = decode_unit(P, u);
+                const UnitInfo U = decode_unit(P, cur, u);
+                PROF_T(qa0);
                 if (PAIR) mbar_wait_backoff_cluster(bar_a_full + 8 * as, aph); else mbar_wait_backoff(bar_a_full + 8 * as, aph);
+                PROF_T(qa1);
+                PROF_ADD(12, qa1 - qa0); PROF_ADD(13, 1);
                 const uint64_t adesc = make_sw128_desc(sA + as * TC_A_BYTES);
                 for (int t = 0; t < U.ntiles_db; t++) {
+                    PROF_T(q0);
                     if (PAIR) {
                         mbar_wait_backoff_cluster(bar_b_full + 8 * bs, bph);
                         mbar_wait_backoff_cluster(bar_t_empty + 8 * ts, tph ^ 1);
                     } else {
                         mbar_wait_backoff(bar_b_full + 8 * bs, bph);
+                        PROF_T(q1);
+                        PROF_ADD(0, q1 - q0);
                         // the accumulator-stage hand-over is on the critical path: poll without sleeping
                         if (BSFM_TC_MMA_SPIN) mbar_wait(bar_t_empty + 8 * ts, tph ^ 1); else mbar_wait_backoff(bar_t_empty + 8 * ts, tph ^ 1);
                     }
+                    PROF_T(q2);
                     tc_fence_after();
                     const uint64_t bdesc = make_sw128_desc(sB + bs * BSLOT);
                     const uint32_t tmem_d = tmem_base + ts * TILE_DB;
@@ -500,6 +555,8 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                     else { tc_commit(bar_b_empty + 8 * bs); tc_commit(bar_t_full + 8 * ts); }
                     if (++bs == BST) { bs = 0; bph ^= 1; }
                     ts ^= 1; if (ts == 0) tph ^= 1;
+                    PROF_T(q3);
+                    PROF_ADD(1, q2 - q0); PROF_ADD(2, q3 - q2); PROF_ADD(3, 1);   // [1] includes [0]
                 }
                 if (PAIR) tc_commit_pair(bar_a_empty + 8 * as); else tc_commit(bar_a_empty + 8 * as);
                 as ^= 1; if (as == 0) aph ^= 1;
@@ -525,8 +582,10 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
         const uint32_t grp = (uint32_t) part & 1u;        // accumulator stage / tile parity this warp serves
         const int gpart = part >> 1;
         uint32_t gtile = 0, gph = 0;                      // running tile number at unit start, phase of the group's stage
-        for (int u = u_first; u < P.unit_end; u += u_step) {
-            const UnitInfo U = decode_unit(P, u);
+        UnitCursor cur;
+            for (int u = u_first; u < P.unit_end; u += u_step) {
+            const UnitInfo U = decode_unit(P, cur, u);
+            PROF_T(eu0);
             const int na = P.norms[U.a_row0 + row];
             // row state.  exact mode : m1 = smallest chunk-min of t, s2 = second smallest chunk-min, bchunk.
             //             bound mode : m1 = smallest chunk LOWER bound, s2 = second smallest lower bound,
@@ -556,9 +615,34 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                 const uint32_t tlane = tmem_base + ((uint32_t) (quad * 32) << 16) + grp * TILE_DB + gpart * (TILE_DB / GNPART);
                 for (int t = (int) ((grp ^ gtile) & 1u); t < U.ntiles_db; t += 2) {
                     const int *nbs = sNall + t * TILE_DB + gpart * (TILE_DB / GNPART);
+                    PROF_T(e0);
                     mbar_wait(bar_t_full + 8 * grp, gph);
+                    PROF_T(e1);
                     tc_fence_after();
                     uint32_t va[32], vb[32];
+                    auto bookkeep = [&](int vmax, int cb) {
+                        const int chunk_id = t * (TILE_DB / BCHUNK) + gpart * (GNCH * CHUNK / BCHUNK) + cb;
+                        const int lb = vmax * neg2 + nbs[cb * BCHUNK];
+                        const int ub = vmax * neg2 + nbs[cb * BCHUNK + BCHUNK - 1];
+                        const bool nb_best = lb < m1;
+                        s2 = nb_best ? m1 : min(s2, lb);
+                        uo = min(uo, nb_best ? ubb : ub);
+                        ubb = nb_best ? ub : ubb;
+                        bchunk = nb_best ? chunk_id : bchunk;
+                        m1 = min(m1, lb);
+                    };
+                    auto release_stage = [&]() {
+                        tc_fence_before();
+                        __syncwarp();       // one arrival per warp: 32 same-address arrivals per warp would serialise
+                        if (lane == 0) {
+                            if (PAIR) mbar_arrive_cluster(bar_t_empty + 8 * grp, 0);   // the LEADER's MMA overwrites both CTAs' stage
+                            else mbar_arrive(bar_t_empty + 8 * grp);                   // accumulator stage free again
+                        }
+                        gph ^= 1;
+#ifdef BSFM_TC_PROFILE
+                        if (warp == 2 && lane == 0) { PROF_ADD(8, e1 - e0); PROF_ADD(9, clock64() - e1); PROF_ADD(11, 1); }
+#endif
+                    };
                     tmem_ld32(tlane, va);
                     int vmax = 0;
 #pragma unroll
@@ -566,49 +650,17 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                         uint32_t (&v)[32] = (c & 1) ? vb : va;
                         uint32_t (&vn)[32] = (c & 1) ? va : vb;
                         tmem_ld_wait_regs(v);
-                        if (c + 1 < GNCH) {
-                            tmem_ld32(tlane + (c + 1) * CHUNK, vn);
-                        } else {
-                            tc_fence_before();
-                            if (PAIR) {
-                                // one arrival per warp on the LEADER's barrier (its MMA overwrites both CTAs' stage)
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_cluster(bar_t_empty + 8 * grp, 0);
-                            } else {
-                                mbar_arrive(bar_t_empty + 8 * grp);     // accumulator stage free again
-                            }
-                            gph ^= 1;
-                        }
-                        // 3-input MAX (VIMNMX3) over the 32 values: four independent chains
-                        int a0 = max(max((int) v[0], (int) v[1]), vmax);
-                        int a1 = max(max((int) v[2], (int) v[3]), (int) v[4]);
-                        int a2 = max(max((int) v[5], (int) v[6]), (int) v[7]);
-                        int a3 = max(max((int) v[8], (int) v[9]), (int) v[10]);
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            a0 = max(max((int) v[11 + 8 * q], (int) v[12 + 8 * q]), a0);
-                            a1 = max(max((int) v[13 + 8 * q], (int) v[14 + 8 * q]), a1);
-                            a2 = max(max((int) v[15 + 8 * q], (int) v[16 + 8 * q]), a2);
-                            a3 = max(max((int) v[17 + 8 * q], (int) v[18 + 8 * q]), a3);
-                        }
-                        a0 = max(max((int) v[27], (int) v[28]), a0);
-                        a1 = max(max((int) v[29], (int) v[30]), a1);
-                        a2 = max((int) v[31], a2);
-                        vmax = max(max(a0, a1), max(a2, a3));
+                        if (c + 1 < GNCH) tmem_ld32(tlane + (c + 1) * CHUNK, vn);
+                        else release_stage();
+                        vmax = chunk_max(v, vmax);
                         if (((c + 1) * CHUNK) % BCHUNK == 0) {
-                            const int cb = ((c + 1) * CHUNK) / BCHUNK - 1;      // bound chunk inside this part
-                            const int chunk_id = t * (TILE_DB / BCHUNK) + gpart * (GNCH * CHUNK / BCHUNK) + cb;
-                            const int lb = vmax * neg2 + nbs[cb * BCHUNK];
-                            const int ub = vmax * neg2 + nbs[cb * BCHUNK + BCHUNK - 1];
-                            const bool nb_best = lb < m1;
-                            s2 = nb_best ? m1 : min(s2, lb);
-                            uo = min(uo, nb_best ? ubb : ub);
-                            ubb = nb_best ? ub : ubb;
-                            bchunk = nb_best ? chunk_id : bchunk;
-                            m1 = min(m1, lb);
+                            bookkeep(vmax, ((c + 1) * CHUNK) / BCHUNK - 1);
                             vmax = 0;
                         }
                     }
+#ifdef BSFM_TC_PROFILE
+                    if (warp == 2 && lane == 0) PROF_ADD(10, clock64() - e1);   // whole tile after the wait
+#endif
                 }
                 gtile += (uint32_t) U.ntiles_db;
             } else {
@@ -664,6 +716,7 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                 ts ^= 1; if (ts == 0) tph ^= 1;
             }
             }
+            PROF_T(eu1);
             // merge the column parts of every row (parts 1.. -> shared memory -> part 0)
             if (part > 0) { int *x = xch + (part - 1) * 640; x[row] = m1; x[128 + row] = s2; x[256 + row] = bchunk; x[384 + row] = ubb; x[512 + row] = uo; }
             asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory");
@@ -722,6 +775,9 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                     }
                 }
             }
+#ifdef BSFM_TC_PROFILE
+            if (warp == 2 && lane == 0) { PROF_ADD(14, clock64() - eu1); PROF_ADD(15, eu1 - eu0); }
+#endif
         }
     }
 

@@ -10,12 +10,23 @@ from bundler_sfm_b200 import keymatch, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "match_golden.npz")
-KERNELS = {"tc": "0", "dp4a": "1"}
+# every kernel variant of the library runs the whole suite:
+#   tc       tcgen05 kernel, bound epilogue, one CTA per unit (the default)
+#   tc_exact tcgen05 kernel, exact chunk-minimum epilogue (also the path of images > 8192 rows)
+#   tc_pair  tcgen05 cta_group::2 kernel on CTA pairs
+#   dp4a     CUDA-core kernel
+KERNELS = {"tc": {"BSFM_MATCH_KERNEL": "0"},
+           "tc_exact": {"BSFM_MATCH_KERNEL": "0", "BSFM_MATCH_EPILOGUE": "0"},
+           "tc_pair": {"BSFM_MATCH_KERNEL": "0", "BSFM_MATCH_PAIR": "1"},
+           "dp4a": {"BSFM_MATCH_KERNEL": "1"}}
 
 
-@pytest.fixture(params=["tc", "dp4a"])
+@pytest.fixture(params=list(KERNELS))
 def kernel(request, monkeypatch):
-    monkeypatch.setenv("BSFM_MATCH_KERNEL", KERNELS[request.param])
+    for k in ("BSFM_MATCH_KERNEL", "BSFM_MATCH_EPILOGUE", "BSFM_MATCH_PAIR"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in KERNELS[request.param].items():
+        monkeypatch.setenv(k, v)
     return request.param
 
 
@@ -104,11 +115,22 @@ def test_tc_equals_dp4a_at_scale(monkeypatch):
     must satisfy the invariants of the algorithm (ascending query index inside a pair, in-range ids)."""
     sizes = [5000] * 12
     imgs = synth.sift_like_descriptors(len(sizes), sizes, seed=7)
+    for k in ("BSFM_MATCH_KERNEL", "BSFM_MATCH_EPILOGUE", "BSFM_MATCH_PAIR"):
+        monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("BSFM_MATCH_KERNEL", "0")
     p0, c0, m0 = keymatch.key_match_full(imgs, -1, 0.6)
     monkeypatch.setenv("BSFM_MATCH_KERNEL", "1")
     p1, c1, m1 = keymatch.key_match_full(imgs, -1, 0.6)
     assert np.array_equal(c0, c1) and np.array_equal(m0, m1)
+    # the other two tensor-core variants at the same scale
+    monkeypatch.setenv("BSFM_MATCH_KERNEL", "0")
+    for extra in ({"BSFM_MATCH_EPILOGUE": "0"}, {"BSFM_MATCH_PAIR": "1"}):
+        for k, v in extra.items():
+            monkeypatch.setenv(k, v)
+        p2, c2, m2 = keymatch.key_match_full(imgs, -1, 0.6)
+        assert np.array_equal(c0, c2) and np.array_equal(m0, m2), extra
+        for k in extra:
+            monkeypatch.delenv(k)
     assert m0.shape[0] > 1000
     pos = 0
     for (j, i), c in zip(p0, c0):

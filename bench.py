@@ -309,22 +309,32 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
         gc, gm = keymatch.gather_match_table(counts, matches)
         return gm.shape[0]
 
+    from bundler_sfm_b200 import _lib
+    lib = _lib.load_library()
     for _ in range(warmup):
         db.run(b, e, -1, 0.6); gather()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    launches0 = lib.bsfm_kernel_launches()
+    sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
+    # device time: the library times its launches with CUDA events on ITS stream (bsfm_match_last_timing); the
+    # NCCL gather runs on torch's stream and is timed with torch events; wall clock is kept as a cross-check
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    search_ms, total_matches = 0.0, 0
+    search_ms, dev_ms, total_matches = 0.0, 0.0, 0
     t0 = time.perf_counter()
-    ev0.record()
     for _ in range(steps):
         db.run(b, e, -1, 0.6)
+        tm = db.timing()
+        ev0.record()
         total_matches = gather()
-        search_ms += db.timing()["search_ms"]
-    ev1.record()
-    torch.cuda.synchronize()
+        ev1.record()
+        torch.cuda.synchronize()
+        search_ms += tm["search_ms"]
+        dev_ms += tm["total_ms"] + ev0.elapsed_time(ev1)
     wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = lib.bsfm_kernel_launches() - launches0
     if dist is not None:
         dist.barrier()
     # e2e: host descriptors -> upload -> run -> gather -> table on the host
@@ -337,14 +347,15 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - t0
     db2.close()
-    t = torch.tensor([wall, search_ms * 1e-3, e2e_wall], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms * 1e-3, search_ms * 1e-3, e2e_wall, wall], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, search_s, e2e_wall = t[0].item(), t[1].item(), t[2].item()
+    dev_s, search_s, e2e_wall, wall = t[0].item(), t[1].item(), t[2].item(), t[3].item()
     npairs = num_images * (num_images - 1) // 2
     dp = float(npairs) * keys_per_image * keys_per_image
     db.close()
-    return {"desc_pairs_per_s": dp * steps / wall, "image_pairs_per_s": npairs * steps / wall, "ms_per_pass": 1e3 * wall / steps,
+    return {"desc_pairs_per_s": dp * steps / dev_s, "image_pairs_per_s": npairs * steps / dev_s, "ms_per_pass": 1e3 * dev_s / steps,
+            "wall_ms_per_pass": 1e3 * wall / steps, "launches": int(launches), "clocks": clocks,
             "search_kernel_ms_per_pass_max_rank": 1e3 * search_s / steps, "int8_tops_search_kernel": dp * 256 / world / (search_s / steps) / 1e12,
             "e2e_desc_pairs_per_s": dp / e2e_wall, "matches": int(total_matches), "h2d_bytes": int(keys.nbytes), "images": num_images, "keys_per_image": keys_per_image,
             "pairs": npairs, "shard": [int(b), int(e)]}
@@ -361,6 +372,28 @@ def cpu_baseline_ba():
     kind = "reference" if loader.ref_sba() is not None else "port"
     return {"value": out["info"][5] / dt, "unit": "LM iterations/s", "cores": 1, "kind": kind,
             "sample": f"one full run_sfm solve of the config ({int(out['info'][5])} LM iterations, {dt:.1f} s), single thread"}
+
+
+def cpu_baseline_match(budget_s=12.0):
+    """single-thread reference MatchKeys (ANN kd-tree, stock 200-visit cap) on pairs of the workload's image size"""
+    from bundler_sfm_b200 import synth
+    from oracle import loader
+    K = MATCH_CFG["keys_per_image"]
+    imgs = synth.sift_like_descriptors(2, K, seed=7)
+    ref = loader.ref_match() is not None
+    n, t0 = 0, time.perf_counter()
+    while True:
+        if ref:
+            loader.match_pair_ref(imgs[0], imgs[1], 0.6, 200)
+        else:
+            loader.match_pair_port(imgs[0], imgs[1], 0.6)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s:
+            break
+    return {"value": n * K * K / dt, "unit": "descriptor-pairs/s", "cores": 1, "kind": "reference" if ref else "port",
+            "sample": f"{n} image pairs of {K} x {K} keys through the reference MatchKeys (kd-tree build + 200-visit priority search), "
+                      f"{dt:.1f} s, single thread"}
 
 
 def main():
@@ -390,14 +423,14 @@ def main():
     args.warmup = warm
     peaks = load_peaks()
 
-    ba = bench_ba(args, torch, dist, rank, world, dev)
+    ba = bench_ba(args, torch, dist, rank, world, dev) if args.workload == "ba" else None
     match = None
-    if not args.no_match:
+    if not args.no_match or args.workload == "match":
         match = bench_match(args, torch, dist, rank, world, dev, args.match_images, MATCH_CFG["keys_per_image"],
                             steps=max(1, min(args.steps, 3)), warmup=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_ba()
+        cpu = cpu_baseline_ba() if args.workload == "ba" else cpu_baseline_match()
 
     if rank == 0:
         i8_peak = 2.0 * peaks["bf16_tflops"]
@@ -425,7 +458,7 @@ def main():
                 "config": {"workload": "KeyMatchFull config 4: all pairs of 500 images x 5000 SIFT keys, exact 2-NN + ratio 0.6; descriptors (320 MB) exceed L2",
                            **MATCH_CFG},
                 "e2e": {"value": match["e2e_desc_pairs_per_s"], "unit": "descriptor-pairs/s", "h2d_bytes_per_step": match["h2d_bytes"], "d2h_bytes_per_step": match["matches"] * 8},
-                "gpu_launches": ba["launches"], "clocks": ba["clocks"],
+                "gpu_launches": match["launches"], "clocks": match["clocks"],
                 "roofline": {"bound": "tensor", "achieved": match["int8_tops_search_kernel"], "peak": i8_peak, "unit": "TOP/s (int8)",
                              "frac": match["int8_tops_search_kernel"] / i8_peak, "traffic": None,
                              "note": "tcgen05 kind::i8 search kernel; 256 int8 ops per descriptor pair; peak = 2 x bf16 dense, " + peaks["source"]},

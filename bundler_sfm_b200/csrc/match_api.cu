@@ -334,7 +334,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
                 const int nhard = h_cnt[3];
                 db->hard_rows += nhard; db->cand_rows += ncand;
                 if (nhard > 0) {
-                    match_fullscan_kernel<<<(unsigned) (((int64_t) nhard * 32 + 255) / 256), 256, 0, db->stream>>>(P, nhard);
+                    match_fullscan_kernel<<<(unsigned) nhard, 256, 0, db->stream>>>(P, nhard);
                     BSFM_KERNEL_CHECK();
                 }
             }

@@ -885,38 +885,49 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
 }
 
 // ---------------------------------------------------------------------------------------------
-// full scan: one warp per "hard" row (bounds undecided): exact two nearest keys over the whole database
+// full scan: one block per "hard" row (bounds undecided): exact two nearest keys over the whole database
 // image with the definition, final ratio test.  Rare by construction.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) match_fullscan_kernel(MatchParams P, int nhard)
 {
-    const int w = (int) (((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+    // one 256-thread block per hard row: every warp scans a strided eighth of the image, then the warps' top-2 merge
+    __shared__ int s_m1[8], s_m2[8], s_mi[8];
+    const int w = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (w >= nhard) return;
     const int slot = P.hard[w];
     const int qrow = P.hard[(size_t) P.cand_cap + w];
     const int u = P.unit_begin + (slot >> 7);
     const RunImage R = P.run_imgs[find_run_image(P.run_imgs, P.num_run_imgs, u)];
-    int m1 = INT_MAX, m2 = INT_MAX, mi = -1;
-    for (int c = lane; c < R.n; c += 32) {
+    int m1 = INT_MAX, m2 = INT_MAX, mi = INT_MAX;
+    for (int c = threadIdx.x; c < R.n; c += 256) {
         const int d = sqdist_rows(P.keys_sw, qrow, (int64_t) R.db_row0 + c);
         if (d < m1) { m2 = m1; m1 = d; mi = c; } else if (d < m2) m2 = d;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        int o1 = __shfl_xor_sync(0xffffffffu, m1, o);
-        int o2 = __shfl_xor_sync(0xffffffffu, m2, o);
-        int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-        int hi = max(m1, o1);
-        int lo2 = min(m2, o2);
-        if (o1 < m1 || (o1 == m1 && oi >= 0 && (mi < 0 || oi < mi))) mi = oi;
+    // (value, index) top-2 merge; ties keep the smaller index (any tie of the two best fails the ratio test anyway)
+    auto merge = [&](int o1, int o2, int oi) {
+        const int hi = max(m1, o1);
+        const int lo2 = min(m2, o2);
+        if (o1 < m1 || (o1 == m1 && oi < mi)) mi = oi;
         m1 = min(m1, o1);
         m2 = min(hi, lo2);
+    };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int o1 = __shfl_xor_sync(0xffffffffu, m1, o);
+        const int o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        merge(o1, o2, oi);
     }
-    if (lane == 0 && (double) m1 < P.ratio_sq * (double) m2) {
-        int pos = atomicAdd(&P.counters[1], 1);
-        if (pos < P.match_cap) { P.match_slot[pos] = match_sort_key(P, R, qrow); P.match_idx2[pos] = mi; }
-        else P.counters[2] = 1;
+    if (lane == 0) { s_m1[warp] = m1; s_m2[warp] = m2; s_mi[warp] = mi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; q++) merge(s_m1[q], s_m2[q], s_mi[q]);
+        if ((double) m1 < P.ratio_sq * (double) m2) {
+            int pos = atomicAdd(&P.counters[1], 1);
+            if (pos < P.match_cap) { P.match_slot[pos] = match_sort_key(P, R, qrow); P.match_idx2[pos] = mi; }
+            else P.counters[2] = 1;
+        }
     }
 }
 

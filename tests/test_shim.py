@@ -14,7 +14,10 @@ from bundler_sfm_b200 import bundle, synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "shim", "_build")
 KM = os.path.join(BUILD, "KeyMatchFull_b200")
+KMP = os.path.join(BUILD, "KeyMatchFull_b200_persistent")
+KEYFILE = os.path.join(BUILD, "libkeyfile_b200.so")
 SFMDRV = os.path.join(BUILD, "libsfmdrv_b200.so")
+REFMATCH = os.path.join(ROOT, "oracle", "_ref", "libref_match.so")
 
 
 def test_sfmdrv_shim_exports_run_sfm():
@@ -29,6 +32,83 @@ def test_keymatchfull_shim_binary_links_reference_main():
         pytest.skip("shim/_build/KeyMatchFull_b200 not built (needs /root/reference at build time)")
     r = subprocess.run([KM], capture_output=True, text=True)
     assert "Usage:" in r.stdout and "<list.txt> <outfile> [window_radius]" in r.stdout   # KeyMatchFull.cpp:65
+
+
+def _read_with(fn, path):
+    """call an `int f(const char *filename, unsigned char **keys[, keypt_t **info])` reader, return the descriptors"""
+    buf = ctypes.POINTER(ctypes.c_ubyte)()
+    fn.restype = ctypes.c_int
+    n = fn(path.encode(), ctypes.byref(buf), None)
+    if n <= 0:
+        return n, None
+    return n, np.ctypeslib.as_array(buf, shape=(n * 128,)).reshape(n, 128).copy()
+
+
+def test_key_reader_equals_reference_readkeyfile(tmp_path):
+    """shim/keyfile_b200.cpp against the unmodified reference parser (src/keys2a.cpp:87-323 compiled in
+    oracle/_ref): plain file, gzip fallback, empty image, missing file, bad descriptor length."""
+    if not (os.path.exists(KEYFILE) and os.path.exists(REFMATCH)):
+        pytest.skip("shim/_build or oracle/_ref not built")
+    import gzip
+    ours = ctypes.CDLL(KEYFILE).bsfm_shim_read_key_file
+    ref = getattr(ctypes.CDLL(REFMATCH), "_Z11ReadKeyFilePKcPPhPP7keypt_t")
+    imgs = synth.sift_like_descriptors(3, [257, 1, 40], seed=5)
+    for i, d in enumerate(imgs):
+        p = str(tmp_path / f"a{i}.key")
+        synth.write_key_file(p, d, seed=i)
+        n0, k0 = _read_with(ref, p)
+        n1, k1 = _read_with(ours, p)
+        assert n0 == n1 == d.shape[0] and np.array_equal(k0, k1) and np.array_equal(k1, d)
+    # gzip fallback: only <name>.gz exists (keys2a.cpp:93-104)
+    p = str(tmp_path / "z.key")
+    synth.write_key_file(p, imgs[0], seed=9)
+    with open(p, "rb") as f, gzip.open(p + ".gz", "wb") as g:
+        g.write(f.read())
+    os.remove(p)
+    n0, k0 = _read_with(ref, p)
+    n1, k1 = _read_with(ours, p)
+    assert n0 == n1 == 257 and np.array_equal(k0, k1)
+    # empty image, missing file, wrong descriptor length: both return 0
+    (tmp_path / "e.key").write_text("0 128\n")
+    (tmp_path / "bad.key").write_text("1 64\n" + "1 2 3 4\n" + " ".join(["7"] * 64) + "\n")
+    for name in ("e.key", "missing.key", "bad.key"):
+        assert _read_with(ref, str(tmp_path / name))[0] == 0
+        assert _read_with(ours, str(tmp_path / name))[0] == 0
+
+
+def test_persistent_keymatchfull_cli_usage():
+    if not os.path.exists(KMP):
+        pytest.skip("shim/_build/KeyMatchFull_b200_persistent not built")
+    r = subprocess.run([KMP], capture_output=True, text=True)
+    assert r.returncode != 0 and "Usage:" in r.stdout and "<list.txt> <outfile> [window_radius]" in r.stdout
+
+
+@pytest.mark.gpu
+def test_persistent_keymatchfull_cli_writes_oracle_table(tmp_path, oracle):
+    """KeyMatchFull's command line on the persistent matcher -> byte-identical matches.init.txt"""
+    if not os.path.exists(KMP):
+        pytest.skip("shim/_build/KeyMatchFull_b200_persistent not built")
+    import gzip
+    sizes = [700, 350, 0, 380, 300, 1200]
+    imgs = synth.sift_like_descriptors(len(sizes), sizes, seed=23)
+    names = []
+    for i, d in enumerate(imgs):
+        p = tmp_path / f"img{i}.key"
+        synth.write_key_file(str(p), d, seed=i)
+        if i == 3:      # this one only exists gzipped
+            with open(p, "rb") as f, gzip.open(str(p) + ".gz", "wb") as g:
+                g.write(f.read())
+            os.remove(p)
+        names.append(str(p))
+    lst = tmp_path / "list_keys.txt"
+    lst.write_text("\n".join(names) + "\n\n")
+    for window, extra in ((-1, []), (2, ["2"])):
+        out = tmp_path / f"matches_{window}.txt"
+        r = subprocess.run([KMP, str(lst), str(out)] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        want, _ = oracle.match_all_pairs_port(imgs, window, 0.6, 16)
+        assert out.read_text() == want
+        assert "[KeyMatchFull] Reading keys took" in r.stdout
 
 
 @pytest.mark.gpu

@@ -67,7 +67,7 @@ def _bind_run_sfm(fn):
 def call_run_sfm(fn, scene, est_focal_length=1, undistort=1, explicit_camera_centers=1, ncons=0, eps2=1e-12,
                  use_constraints=0, constrained=None, constraints=None, weights=None,
                  use_point_constraints=0, points_constraints=None, point_constraint_weight=0.0,
-                 extra_info=False, export=False):
+                 extra_info=False, export=False, fix_points=0):
     """Calls a run_sfm-shaped C function (ours or the reference's) on a scene dict (synth.ba_scene).
     Returns a dict with the refined R, c, f, k, pts (+ info when the callee provides it)."""
     vmask = np.ascontiguousarray(scene["vmask"], dtype=np.int8)
@@ -85,7 +85,7 @@ def call_run_sfm(fn, scene, est_focal_length=1, undistort=1, explicit_camera_cen
         ex = {"V": np.zeros((n, 9)), "S": np.zeros((m * cnp, m * cnp)), "U": np.zeros((m, cnp * cnp)), "W": np.zeros((m * cnp, 3 * n))}
     args = [n, m, ncons, vmask.ctypes.data, proj.ctypes.data, est_focal_length, 0, undistort, explicit_camera_centers,
             ctypes.addressof(cams), pts.ctypes.data, use_constraints, use_point_constraints,
-            pc.ctypes.data if pc is not None else None, float(point_constraint_weight), 0, 0, float(eps2),
+            pc.ctypes.data if pc is not None else None, float(point_constraint_weight), int(fix_points), 0, float(eps2),
             ex["V"].ctypes.data if export and "V" in export_keys else None, ex["S"].ctypes.data if export and "S" in export_keys else None,
             ex["U"].ctypes.data if export and "U" in export_keys else None, ex["W"].ctypes.data if export and "W" in export_keys else None]
     info = np.zeros(10)

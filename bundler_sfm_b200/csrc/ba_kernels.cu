@@ -509,7 +509,7 @@ __global__ void grad_stats_kernel(Problem P, const double *p)
     const int cnp = P.M.cnp;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     double inf = 0.0, pl2 = 0.0, md = DBL_MIN;
-    if (q < P.nvars) {
+    if (q < P.nlm) {
         inf = fabs(P.eab[q]);
         pl2 = p[q] * p[q];
         if (q < P.m * cnp) {
@@ -767,6 +767,54 @@ __global__ void backsub_kernel(Problem P, const double *da)
 }
 
 // ------------------------------------------------------------------------------------------------
+// motion-only BA (sba_mot_levmar_x, sba_levmar.c:2495-2514): the augmented normal equations are block diagonal,
+// (U_j + mu I) da_j = ea_j per camera, solved like sba_Axb_Chol (Cholesky, failure on a non-positive pivot).
+// One thread per camera (cnp <= 9).
+// ------------------------------------------------------------------------------------------------
+__global__ void mot_solve_kernel(Problem P)
+{
+    cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.m) return;
+    const int cnp = P.M.cnp;
+    double *da = P.dp + (size_t) j * cnp;
+    if (j < P.mcon) {
+        for (int ii = 0; ii < cnp; ii++) da[ii] = 0.0;
+        return;
+    }
+    const double mu = *P.mu;
+    double L[9][9], y[9];
+    const double *Uj = P.U + (size_t) j * cnp * cnp;
+    for (int ii = 0; ii < cnp; ii++)
+        for (int jj = 0; jj < cnp; jj++) L[ii][jj] = Uj[ii * cnp + jj] + (ii == jj ? mu : 0.0);
+    bool ok = true;
+    for (int c = 0; c < cnp && ok; c++) {
+        double d = L[c][c];
+        for (int k = 0; k < c; k++) d -= L[c][k] * L[c][k];
+        if (!(d > 0.0)) { ok = false; break; }     // dpotrf: not positive definite
+        d = sqrt(d);
+        L[c][c] = d;
+        for (int r = c + 1; r < cnp; r++) {
+            double v = L[r][c];
+            for (int k = 0; k < c; k++) v -= L[r][k] * L[c][k];
+            L[r][c] = v / d;
+        }
+    }
+    if (!ok) { P.sc->chol_fail = 1; return; }
+    const double *ea = P.eab + (size_t) j * cnp;
+    for (int r = 0; r < cnp; r++) {
+        double v = ea[r];
+        for (int k = 0; k < r; k++) v -= L[r][k] * y[k];
+        y[r] = v / L[r][r];
+    }
+    for (int r = cnp - 1; r >= 0; r--) {
+        double v = y[r];
+        for (int k = r + 1; k < cnp; k++) v -= L[k][r] * da[k];
+        da[r] = v / L[r][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K8b: pdp = p + dp, ||dp||^2, dL = sum dp (mu dp + J^T e)   (sba_levmar.c:1443-1447, 1524-1525)
 // ------------------------------------------------------------------------------------------------
 __global__ void update_kernel(Problem P, const double *p, double *pdp)
@@ -775,11 +823,13 @@ __global__ void update_kernel(Problem P, const double *p, double *pdp)
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const double mu = *P.mu;
     double d2 = 0.0, dl = 0.0;
-    if (q < P.nvars) {
+    if (q < P.nlm) {
         const double d = P.dp[q];
         pdp[q] = p[q] + d;
         d2 = d * d;
         dl = d * (mu * d + P.eab[q]);
+    } else if (q < P.nvars) {
+        pdp[q] = p[q];      // motion-only BA: the points are not unknowns
     }
     double out;
     if (grid_reduce<0>(d2, P.partial, P.ticket, out)) P.sc->dp_L2 = out;

@@ -42,6 +42,7 @@ struct Scalars {
 
 struct Problem {
     int n, m, mcon, nvis, nvars, Sdim;
+    int nlm;              // LM unknowns: nvars (motion+structure) or m*cnp (motion only, sba_mot_levmar_x: points stay fixed)
     Model M;
     // structure (device)
     const int *rowptr;    // n+1, point-major CRS (idxij.rowptr)

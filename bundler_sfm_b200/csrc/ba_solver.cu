@@ -37,6 +37,7 @@ __global__ void chunk_count_kernel(const int *, int, int *);
 __global__ void zero_kernel(double *, size_t);
 __global__ void backsub_kernel(Problem, const double *);
 __global__ void update_kernel(Problem, const double *, double *);
+__global__ void mot_solve_kernel(Problem);
 __global__ void vmask_count_kernel(const char *, int, int, int *);
 __global__ void vmask_fill_kernel(const char *, int, int, const int *, int *, int *);
 __global__ void tuple_count_kernel(int, int, const int *, const int *, int *);
@@ -163,17 +164,22 @@ struct PhaseTimer {
         BSFM_KERNEL_CHECK();                                                                            \
     } while (0)
 
-extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,
-                                            const double *x, const double *covx, int mnp,
-                                            const bsfm_sfm_model_t *model, int jac_mode,
-                                            int itmax, int verbose, const double opts[6], double info[10],
-                                            int use_constraints, const bsfm_camera_constraints_t *constraints,
-                                            int use_point_constraints, const bsfm_point_constraints_t *point_constraints,
-                                            double *Vout, double *Sout, double *Uout, double *Wout)
+// Shared implementation of the two LM drivers.
+//   mot == 0 : sba_motstr_levmar_x (cameras + points), p = (a_1..a_m, b_1..b_n)
+//   mot == 1 : sba_mot_levmar_x (sba_levmar.c:2090-2690; cameras only), p = (a_1..a_m), the points are read from
+//              `fixed_pts` (n x 3; what sfm_project_point3_mot takes from its adata, sfm.c:553-560) and never change
+static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,
+                       const double *x, const double *covx, int mnp,
+                       const bsfm_sfm_model_t *model, int jac_mode,
+                       int itmax, int verbose, const double opts[6], double info[10],
+                       int use_constraints, const bsfm_camera_constraints_t *constraints,
+                       int use_point_constraints, const bsfm_point_constraints_t *point_constraints,
+                       double *Vout, double *Sout, double *Uout, double *Wout)
 {
     clear_error();
     TRY(require_device());
-    if (n <= 0 || m <= 0 || mcon < 0 || mcon >= m || !vmask || !p || !x || !model || !opts) {
+    const char *const fname = mot ? "sba_mot_levmar_x" : "sba_motstr_levmar_x";
+    if (n <= 0 || m <= 0 || mcon < 0 || mcon >= m || !vmask || !p || !x || !model || !opts || (mot && !fixed_pts)) {
         set_error("bsfm_sba_motstr_levmar_model: bad arguments (n=%d m=%d mcon=%d)", n, m, mcon);
         return BSFM_ERR_ARG;
     }
@@ -227,6 +233,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     P.M.k_idx = P.M.undistort ? (P.M.est_focal ? 7 : 6) : -1;
     P.M.f_scale = model->f_scale; P.M.k_scale = model->k_scale;
     P.nvars = m * cnp + n * 3;
+    P.nlm = mot ? m * cnp : P.nvars;
     P.Sdim = (m - mcon) * cnp;
 
     // ---------------- setup: vmask -> CRS (sba_levmar.c:652-663), camera-major permutation ----------------
@@ -258,9 +265,9 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     BSFM_CUDA_TRY(cudaStreamSynchronize(st));
     P.nvis = nvis;
     const int nobs = nvis * 2;
-    if (nobs < P.nvars) {   // sba_levmar.c:647-650
-        fprintf(stderr, "SBA: sba_motstr_levmar_x() cannot solve a problem with fewer measurements [%d] than unknowns [%d]\n", nobs, P.nvars);
-        set_error("fewer measurements [%d] than unknowns [%d]", nobs, P.nvars);
+    if (nobs < P.nlm) {   // sba_levmar.c:647-650, :2235-2238
+        fprintf(stderr, "SBA: %s() cannot solve a problem with fewer measurements [%d] than unknowns [%d]\n", fname, nobs, P.nlm);
+        set_error("fewer measurements [%d] than unknowns [%d]", nobs, P.nlm);
         return SBA_ERROR_RC;
     }
     int *d_obs_cam, *d_obs_pt, *d_cam_ptr, *d_cam_obs, *d_iota;
@@ -432,7 +439,11 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     TRY(D.alloc(&d_mu, 1));
     P.mu = d_mu;
     Scalars *h_sc = ctx.h_sc;
-    BSFM_CUDA_TRY(cudaMemcpyAsync(d_p, p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_p, p, (size_t) P.nlm * sizeof(double), cudaMemcpyDefault, st));
+    if (mot) {
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_p + P.nlm, fixed_pts, (size_t) n * 3 * sizeof(double), cudaMemcpyDefault, st));
+        BSFM_CUDA_TRY(cudaMemsetAsync(P.dp, 0, (size_t) P.nvars * sizeof(double), st));   // the points' increments stay 0
+    }
     PT.end();
 
     auto read_scalars = [&]() -> int {
@@ -463,7 +474,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     TRY(read_scalars());
     pen = any_constraints ? h_sc->penalty : 0.0;
     p_eL2 = h_sc->e_L2 + pen;    // sba_levmar.c:802-842
-    if (verbose) printf("initial motstr-SBA error %g [%g]\n", p_eL2, p_eL2 / nvis);
+    if (verbose) printf(mot ? "initial mot-SBA error %g [%g]\n" : "initial motstr-SBA error %g [%g]\n", p_eL2, p_eL2 / nvis);
     init_p_eL2 = p_eL2;
     if (!std::isfinite(p_eL2)) stop = 7;
 
@@ -474,7 +485,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         BSFM_KERNEL_CHECK();
         u_partial_kernel<<<m * useg, 128, 0, st>>>(P, d_e, useg);
         BA_LAUNCH(u_final_kernel, m, 96, P, d_p, useg);
-        BA_LAUNCH(v_kernel, (n + 127) / 128, 128, P, d_p, d_e);
+        if (!mot) BA_LAUNCH(v_kernel, (n + 127) / 128, 128, P, d_p, d_e);
         if (Vout) BSFM_CUDA_TRY(cudaMemcpyAsync(Vout, P.V, (size_t) n * 9 * sizeof(double), cudaMemcpyDefault, st));   // :1039-1051
         BA_LAUNCH(grad_stats_kernel, red_blocks_var, 256, P, d_p);
         PT.end();
@@ -489,6 +500,13 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
             BSFM_CUDA_TRY(cudaMemsetAsync(&P.sc->singular_v, 0, 3 * sizeof(int), st));
             *h_mu = mu;
             BSFM_CUDA_TRY(cudaMemcpyAsync(d_mu, h_mu, sizeof(double), cudaMemcpyHostToDevice, st));
+            if (mot) {
+                // block-diagonal system: (U_j + mu I) da_j = ea_j per camera (sba_levmar.c:2487-2514)
+                PT.begin(3);
+                BA_LAUNCH(mot_solve_kernel, (m + 63) / 64, 64, P);
+                PT.end();
+                PT.begin(4);
+            } else {
             PT.begin(2);
             BA_LAUNCH(vinv_kernel, (n + 255) / 256, 256, P);
             if (!s_dense) {   // camera pairs without a common point keep S_jk = 0
@@ -502,23 +520,24 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
             PT.end();
             PT.begin(4);
             BA_LAUNCH(backsub_kernel, (std::max(n, m * cnp) + 127) / 128, 128, P, d_da);
+            }
             BA_LAUNCH(update_kernel, red_blocks_var, 256, P, d_p, d_pdp);
             TRY(launch_residual(d_pdp, d_camR_b, d_enew, d_e, eps5));
             PT.end();
             TRY(read_scalars());
 
             bool take_moredamping = true;
-            if (h_sc->singular_v) {
+            if (!mot && h_sc->singular_v) {
                 fprintf(stderr, "SBA: singular matrix V*_i in sba_motstr_levmar_x(), increasing damping\n");   // :1156-1161
             } else {
-                ++nlss;
+                nlss += mot ? (m - mcon) : 1;      // the motion-only routine counts one system per camera (:2513)
                 const bool issolved = !h_sc->chol_fail;
                 if (issolved) {
                     dp_L2 = h_sc->dp_L2;
                     if (dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }                              // :1450-1454
                     if (dp_L2 >= (p_L2 + eps2) / SBA_EPSILON_SQ) {                                 // :1456-1462
-                        fprintf(stderr, "SBA: the matrix of the augmented normal equations is almost singular in sba_motstr_levmar_x(),\n"
-                                        "     minimization should be restarted from the current solution with an increased damping term\n");
+                        fprintf(stderr, "SBA: the matrix of the augmented normal equations is almost singular in %s(),\n"
+                                        "     minimization should be restarted from the current solution with an increased damping term\n", fname);
                         set_error("augmented normal equations almost singular");
                         return SBA_ERROR_RC;
                     }
@@ -540,10 +559,12 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
                         mu = mu * ((tmp >= SBA_ONE_THIRD) ? tmp : SBA_ONE_THIRD);
                         nu = 2;
                         const double max_pct_change = h_sc->max_pct;
-                        printf("max_pct_change: %0.3e\n", max_pct_change);                         // :1563 (unconditional)
-                        fflush(stdout);
-                        if (pdp_eL2 - 2.0 * sqrt(p_eL2 * pdp_eL2) < (eps4_sq - 1.0) * p_eL2) stop = 4;
-                        if (max_pct_change < eps5 && itno >= 4) { stop = 8; break; }               // :1569-1572 (step discarded)
+                        if (!mot) {     // Snavely's stop-8 statistic exists only in the motion+structure routine
+                            printf("max_pct_change: %0.3e\n", max_pct_change);                     // :1563 (unconditional)
+                            fflush(stdout);
+                        }
+                        if (pdp_eL2 - 2.0 * sqrt(p_eL2 * pdp_eL2) < (eps4_sq - 1.0) * p_eL2) stop = 4;   // :1567, :2596
+                        if (!mot && max_pct_change < eps5 && itno >= 4) { stop = 8; break; }       // :1569-1572 (step discarded)
                         std::swap(d_p, d_pdp); std::swap(d_e, d_enew); std::swap(d_camR_a, d_camR_b);
                         p_eL2 = pdp_eL2;
                         if (any_constraints) { BA_LAUNCH(penalty_kernel, 1, 32, P, d_p); BSFM_KERNEL_CHECK(); }
@@ -556,7 +577,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
             mu *= nu;
             nu2 = nu << 1;
             if (nu2 <= nu) {
-                fprintf(stderr, "SBA: too many failed attempts to increase the damping factor in sba_motstr_levmar_x()! Singular Hessian matrix?\n");
+                fprintf(stderr, "SBA: too many failed attempts to increase the damping factor in %s()! Singular Hessian matrix?\n", fname);
                 stop = 6;
                 break;
             }
@@ -593,7 +614,7 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
         BA_LAUNCH(schur_final_kernel, (nblocks * 32 + 127) / 128, 128, P);
         BSFM_CUDA_TRY(cudaMemcpyAsync(Sout, P.S, (size_t) Sdim * Sdim * sizeof(double), cudaMemcpyDefault, st));   // symmetric: transpose == itself (:2017-2025)
     }
-    BSFM_CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t) P.nvars * sizeof(double), cudaMemcpyDefault, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(p, d_p, (size_t) P.nlm * sizeof(double), cudaMemcpyDefault, st));
     BSFM_CUDA_TRY(cudaEventRecord(ev_end, st));
     BSFM_CUDA_TRY(cudaStreamSynchronize(st));
     if (info) {   // :2028-2049
@@ -605,6 +626,28 @@ extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *
     g_timing.iterations = itno;
     g_timing.launches = (int) (g_kernel_launches.load() - launches0);
     return (stop != 7) ? itno : SBA_ERROR_RC;
+}
+
+extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,
+                                            const double *x, const double *covx, int mnp,
+                                            const bsfm_sfm_model_t *model, int jac_mode,
+                                            int itmax, int verbose, const double opts[6], double info[10],
+                                            int use_constraints, const bsfm_camera_constraints_t *constraints,
+                                            int use_point_constraints, const bsfm_point_constraints_t *point_constraints,
+                                            double *Vout, double *Sout, double *Uout, double *Wout)
+{
+    return levmar_impl(0, nullptr, n, m, mcon, vmask, p, cnp, pnp, x, covx, mnp, model, jac_mode, itmax, verbose, opts, info,
+                       use_constraints, constraints, use_point_constraints, point_constraints, Vout, Sout, Uout, Wout);
+}
+
+extern "C" int bsfm_sba_mot_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp,
+                                         const double *x, const double *covx, int mnp,
+                                         const bsfm_sfm_model_t *model, const double *points, int jac_mode,
+                                         int itmax, int verbose, const double opts[6], double info[10],
+                                         int use_constraints, const bsfm_camera_constraints_t *constraints)
+{
+    return levmar_impl(1, points, n, m, mcon, vmask, p, cnp, 3, x, covx, mnp, model, jac_mode, itmax, verbose, opts, info,
+                       use_constraints, constraints, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int bsfm_ba_last_timing(float ms[6], int *iterations, int *launches)
@@ -624,7 +667,7 @@ extern "C" int bsfm_run_sfm(int num_pts, int num_cameras, int ncons, char *vmask
                             double *Vout, double *Sout, double *Uout, double *Wout, double *info_out)
 {
     clear_error();
-    if (fix_points) { set_error("bsfm_run_sfm: fix_points=1 (sba_mot_levmar, motion-only BA) is outside the GPU path"); return BSFM_ERR_UNSUPPORTED; }
+    if (fix_points && (Vout || Sout || Uout || Wout)) { set_error("bsfm_run_sfm: fix_points=1 has no V/S/U/W export (nor has the reference, sfm.c:843-856)"); return BSFM_ERR_UNSUPPORTED; }
     if (optimize_for_fisheye) { set_error("bsfm_run_sfm: optimize_for_fisheye=1 is outside the GPU path"); return BSFM_ERR_UNSUPPORTED; }
     if (est_focal_length && const_focal_length) { set_error("bsfm_run_sfm: const_focal_length is not implemented (nor in the reference, sfm.c:518-521)"); return BSFM_ERR_UNSUPPORTED; }
     if (num_pts <= 0 || num_cameras <= 0 || !vmask || !projections || !init_camera_params || !init_pts) {
@@ -709,7 +752,13 @@ extern "C" int bsfm_run_sfm(int num_pts, int num_cameras, int ncons, char *vmask
 
     const char *verb_env = getenv("BSFM_BA_VERBOSE");
     const int verbosity = verb_env ? atoi(verb_env) : 3;          // VERBOSITY 3, MAX_ITERS 150 (sfm.c:814-815)
-    int rc = bsfm_sba_motstr_levmar_model(num_pts, num_cameras, ncons, vmask, params.data(), cnp, 3, projections, nullptr, 2,
+    int rc;
+    if (fix_points)     // sfm.c:843-849: motion-only BA, the points come from init_pts and stay as they are
+        rc = bsfm_sba_mot_levmar_model(num_pts, num_cameras, ncons, vmask, params.data(), cnp, projections, nullptr, 2,
+                                       &model, params.data() + num_camera_params, BSFM_BA_JAC_FD, 150, verbosity, opts, info,
+                                       use_constraints, use_constraints ? constraints.data() : nullptr);
+    else
+        rc = bsfm_sba_motstr_levmar_model(num_pts, num_cameras, ncons, vmask, params.data(), cnp, 3, projections, nullptr, 2,
                                           &model, BSFM_BA_JAC_FD, 150, verbosity, opts, info,
                                           use_constraints, use_constraints ? constraints.data() : nullptr,
                                           use_point_constraints, use_point_constraints ? point_constraints.data() : nullptr,

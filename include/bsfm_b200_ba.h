@@ -89,12 +89,26 @@ int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, doub
                                  int use_point_constraints, const bsfm_point_constraints_t *point_constraints,
                                  double *Vout, double *Sout, double *Uout, double *Wout);
 
+/* Motion-only solver == sba_mot_levmar_x (lib/sba-1.5/sba.h:157-166, lib/sba-1.5/sba_levmar.c:2090-2690) with
+ * func/fjac/adata replaced by the explicit camera model: only the cameras are unknowns, the n points are read from
+ * `points` (n x 3, host or device; what sfm_project_point3_mot takes from its adata, lib/sfm-driver/sfm.c:553-560)
+ * and never change.  p = (a_1..a_m) in/out.  The augmented normal equations are block diagonal,
+ * (U_j + mu I) da_j = ea_j per camera (sba_levmar.c:2487-2514).  The LM controller is the stock SBA one: it has no
+ * stop-8 rule and prints no max_pct_change; info[9] counts one linear system per camera and try (:2513).
+ * Returns like bsfm_sba_motstr_levmar_model.                                                                    */
+int bsfm_sba_mot_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp,
+                              const double *x, const double *covx, int mnp,
+                              const bsfm_sfm_model_t *model, const double *points, int jac_mode,
+                              int itmax, int verbose, const double opts[6], double info[10],
+                              int use_constraints, const bsfm_camera_constraints_t *constraints);
+
 /* == run_sfm (lib/sfm-driver/sfm.h:68-86): same arguments, same in/out semantics
  * (init_camera_params and init_pts are overwritten with the solution, sfm.c:876-929; prints
  * "[run_sfm] Number of iterations" / "info[6]" like sfm.c:872-873), plus `info_out` (nullable,
  * 10 doubles) and an int return (0 or negative error) which the void reference lacks.
- * GPU path covers fix_points == 0, optimize_for_fisheye == 0, const_focal_length == 0 and cameras
- * with known_intrinsics == 0; anything else returns BSFM_ERR_UNSUPPORTED.                       */
+ * fix_points == 1 runs the motion-only solver (sfm.c:843-849; init_pts untouched).  GPU path covers
+ * optimize_for_fisheye == 0, const_focal_length == 0 and cameras with known_intrinsics == 0; anything else
+ * returns BSFM_ERR_UNSUPPORTED.                                                                 */
 int bsfm_run_sfm(int num_pts, int num_cameras, int ncons, char *vmask, double *projections,
                  int est_focal_length, int const_focal_length, int undistort, int explicit_camera_centers,
                  bsfm_camera_params_t *init_camera_params, bsfm_v3_t *init_pts,

@@ -5,6 +5,7 @@
  *     lib/sfm-driver/sfm.c:1016-1100)
  *   - ref_hook_sba_motstr_levmar: sfm.c is compiled with -Dsba_motstr_levmar=<this> so the
  *     info[10] vector that run_sfm only prints (sfm.c:872-873) can be read back by tests.
+ *   - ref_hook_sba_mot_levmar: the same for the motion-only call (fix_points = 1, sfm.c:843-856).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,6 +33,22 @@ int ref_hook_sba_motstr_levmar(const int n, const int m, const int mcon, char *v
     g_last_ret = sba_motstr_levmar(n, m, mcon, vmask, p, cnp, pnp, x, covx, mnp, proj, projac,
                                    adata, itmax, verb, opts, info, use_constraints, constraints,
                                    use_point_constraints, point_constraints, Vout, Sout, Uout, Wout);
+    memcpy(g_last_info, info, sizeof(g_last_info));
+    return g_last_ret;
+}
+
+int ref_hook_sba_mot_levmar(const int n, const int m, const int mcon, char *vmask,
+        double *p, const int cnp, double *x, double *covx, const int mnp,
+        void (*proj)(int j, int i, double *aj, double *xij, void *adata),
+        void (*projac)(int j, int i, double *aj, double *Aij, void *adata),
+        void *adata, const int itmax, const int verbose, const double opts[SBA_OPTSSZ],
+        double info[SBA_INFOSZ], int use_constraints, camera_constraints_t *constraints)
+{
+    int verb = verbose;
+    const char *q = getenv("REF_SBA_VERBOSE");
+    if (q) verb = atoi(q);
+    g_last_ret = sba_mot_levmar(n, m, mcon, vmask, p, cnp, x, covx, mnp, proj, projac,
+                                adata, itmax, verb, opts, info, use_constraints, constraints);
     memcpy(g_last_info, info, sizeof(g_last_info));
     return g_last_ret;
 }

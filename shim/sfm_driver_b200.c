@@ -8,7 +8,7 @@
  *     ... -o bundler ... sfm_driver_b200.o -L<repo>/bundler_sfm_b200 -lbsfm_b200   (instead of -lsfmdrv -lsba.v1.5)
  *
  * The struct arguments are layout-identical (include/bsfm_b200_ba.h restates camera_params_t / v3_t).
- * Options the GPU path does not cover (fix_points, fisheye) terminate like the reference's own fatal
+ * Options the GPU path does not cover (fisheye, known_intrinsics) terminate like the reference's own fatal
  * paths do (printf + exit(1), sfm.c:56-73): there is deliberately no silent CPU fallback.
  */
 #include <stdio.h>

@@ -125,7 +125,11 @@ def test_unsupported_options_fail_loudly():
     pts = scene["pts"].copy()
     proj = np.ascontiguousarray(scene["projections"])
     rc = fn(60, 4, 0, vmask.ctypes.data, proj.ctypes.data, 1, 0, 1, 1, ctypes.addressof(cams), pts.ctypes.data,
-            0, 0, None, 0.0, 1, 0, 1e-12, None, None, None, None, None)   # fix_points = 1
+            0, 0, None, 0.0, 0, 1, 1e-12, None, None, None, None, None)   # optimize_for_fisheye = 1
+    assert rc == -6 and b"fisheye" in lib.bsfm_last_error()
+    S = np.zeros((36, 36))
+    rc = fn(60, 4, 0, vmask.ctypes.data, proj.ctypes.data, 1, 0, 1, 1, ctypes.addressof(cams), pts.ctypes.data,
+            0, 0, None, 0.0, 1, 0, 1e-12, None, S.ctypes.data, None, None, None)   # fix_points = 1 with an export buffer
     assert rc == -6 and b"fix_points" in lib.bsfm_last_error()
 
 
@@ -191,3 +195,57 @@ def test_export_of_U_V_W_S_vs_reference(oracle):
             # same gate as the parameters: the blocks are evaluated at solutions that agree to ~1e-7 and S = U - Y W^T cancels
             assert np.max(np.abs(got[key] - ref[key])) <= PARAM_TOL * scale, (m, key, np.max(np.abs(got[key] - ref[key])) / scale)
         assert np.allclose(got["S"], got["S"].T)
+
+
+# ------------------------------------------------------------------------------------------------
+# motion-only BA: run_sfm(fix_points = 1) -> sba_mot_levmar (sfm.c:843-849, sba_levmar.c:2090-2690)
+# ------------------------------------------------------------------------------------------------
+MOT_GOLD = os.path.join(os.path.dirname(__file__), "golden", "ba_mot_golden.npz")
+
+
+def check_mot_solution(got, ref, scene, what):
+    nvis = scene["projections"].shape[0]
+    r_gpu = np.sqrt(got["info"][1] / nvis)
+    r_ref = np.sqrt(ref["info"][1] / nvis)
+    assert abs(r_gpu - r_ref) <= RMSE_TOL, (what, r_gpu, r_ref)
+    # the reference stops these solves through stop rule 4 with eps4 = 0, i.e. when  pdp - 2 sqrt(p pdp) < -p  holds by
+    # ROUNDING at convergence (sba_levmar.c:2596), or through rule 2: the iteration at which that happens is not a
+    # property of the algorithm, so the count may differ by a few while the converged solution must agree
+    assert abs(int(got["info"][5]) - int(ref["info"][5])) <= 3, (what, "iterations", got["info"][5], ref["info"][5])
+    assert int(got["info"][6]) in (2, 4), (what, "stop reason", got["info"][6])
+    assert abs(got["info"][0] - ref["info"][0]) <= 1e-9 * abs(ref["info"][0]), (what, "initial error")
+    for key in ("R", "c", "f"):
+        assert rel_group_err(got[key], ref[key]) <= PARAM_TOL, (what, key, rel_group_err(got[key], ref[key]))
+    assert np.max(np.abs(got["k"] - ref["k"])) * 5.0 <= PARAM_TOL * max(1.0, 5.0 * np.max(np.abs(ref["k"]))), (what, "k")
+    assert np.array_equal(got["pts"], scene["pts"]), (what, "points must stay fixed")
+
+
+@pytest.mark.parametrize("name,kw", [("syn10", {}), ("syn6nf", {"est_focal_length": 0}), ("kermit", {})])
+def test_motion_only_golden(name, kw):
+    g = np.load(MOT_GOLD)
+    scene = gold_scene(g, name)
+    got = bundle.run_sfm(scene, fix_points=1, **kw)
+    ref = {k: g[f"{name}_ref_{k}"] for k in ("R", "c", "f", "k", "info")}
+    check_mot_solution(got, ref, scene, "mot_" + name)
+
+
+def test_motion_only_golden_with_constraints():
+    g = np.load(MOT_GOLD)
+    scene = gold_scene(g, "syn10c")
+    got = bundle.run_sfm(scene, fix_points=1, use_constraints=1, constrained=g["syn10c_constrained"],
+                         constraints=g["syn10c_constraints"], weights=g["syn10c_weights"])
+    ref = {k: g[f"syn10c_ref_{k}"] for k in ("R", "c", "f", "k", "info")}
+    check_mot_solution(got, ref, scene, "mot_syn10c")
+
+
+def test_motion_only_fresh_scene_vs_reference(oracle):
+    """a larger motion-only solve against the unmodified reference run on the GPU box (oracle/_ref travels)"""
+    from oracle import loader
+    if loader.ref_sba() is None:
+        pytest.skip("oracle/_ref/libref_sba.so not available (the C restatement has no motion-only mode)")
+    scene = synth.ba_scene(40, 6000, 5, seed=31)
+    got = bundle.run_sfm(scene, fix_points=1)
+    ref = loader.run_sfm_ref(scene, fix_points=1)
+    check_mot_solution(got, ref, scene, "mot_fresh40")
+    assert got["info"][1] < got["info"][0]
+    assert got["info"][9] == 40 * (got["info"][7] - 1)     # one linear system per camera and function evaluation (:2513)

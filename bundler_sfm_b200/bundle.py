@@ -198,3 +198,33 @@ def levmar_model(n, m, vmask_ptr, p_ptr, x_ptr, cnp, R_init, f_fixed, est_focal_
     if rc < -1:
         check(rc, "bsfm_sba_motstr_levmar_model")
     return rc, info
+
+
+def reprojection_outliers(scene, estimate_distortion=1, min_thresh=8.0, max_thresh=16.0, pt_protected=None, cap=None):
+    """bsfm_reprojection_outliers: the statistics / outlier pass BundlerApp::RunSFM_SBA runs after every run_sfm
+    (src/Bundle.cpp:659-856) on a scene dict (vmask, projections, R, c, f, k, pts).  Defaults are bundler's
+    m_min/max_proj_error_threshold (BundlerApp.h).  Returns dist[nvis], stats[m x 5] (n, mean, median, med80, thresh),
+    outliers, errors, global_mean."""
+    lib = load_library()
+    fn = lib.bsfm_reprojection_outliers
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                   ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                   ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    vmask = np.ascontiguousarray(scene["vmask"], dtype=np.int8)
+    n, m = vmask.shape
+    proj = np.ascontiguousarray(scene["projections"], dtype=np.float64)
+    cams = make_cameras(scene["R"], scene["c"], scene["f"], scene["k"])
+    pts = np.ascontiguousarray(scene["pts"], dtype=np.float64)
+    prot = None if pt_protected is None else np.ascontiguousarray(pt_protected, dtype=np.int8)
+    nvis = proj.shape[0]
+    cap = n if cap is None else int(cap)
+    stats = np.zeros((m, 5)); dist = np.zeros(nvis)
+    out_idx = np.zeros(max(cap, 1), np.int32); out_err = np.zeros(max(cap, 1))
+    gm = ctypes.c_double()
+    rc = fn(n, m, vmask.ctypes.data, proj.ctypes.data, ctypes.addressof(cams), pts.ctypes.data, int(estimate_distortion),
+            float(min_thresh), float(max_thresh), None if prot is None else prot.ctypes.data, stats.ctypes.data, dist.ctypes.data,
+            out_idx.ctypes.data, out_err.ctypes.data, cap, ctypes.byref(gm))
+    check(rc, "bsfm_reprojection_outliers")
+    k = min(rc, cap)
+    return {"dist": dist, "stats": stats, "outliers": out_idx[:k].copy(), "errors": out_err[:k].copy(), "global_mean": gm.value, "count": rc}

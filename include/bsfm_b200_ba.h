@@ -116,6 +116,28 @@ int bsfm_run_sfm(int num_pts, int num_cameras, int ncons, char *vmask, double *p
                  double point_constraint_weight, int fix_points, int optimize_for_fisheye, double eps2,
                  double *Vout, double *Sout, double *Uout, double *Wout, double *info_out);
 
+/* The reprojection statistics / outlier pass BundlerApp::RunSFM_SBA runs after every run_sfm on the same
+ * vmask / projections / cameras / points (src/Bundle.cpp:659-856), as one call:
+ *   dist(obs)   = || sfm_project_rd(camera, point, estimate_distortion, explicit centres) - measurement ||  (:721-754)
+ *   per camera  : med80 = kth_element_copy(n, iround(0.8 n), dists) (0.0 when that index is >= n, lib/imagelib/
+ *                 qsort.c:191-194), thresh = CLAMP(1.2 * 2.0 * med80, min_thresh, max_thresh)  (:761-771)
+ *   outliers    : every point with dist > thresh in some camera, unless pt_protected[point] != 0 (the caller's
+ *                 "constrained point" rule, :801-806); the reported error is the distance in the first (lowest
+ *                 index) camera that flags the point, like the reference's first-found rule (:809-821)
+ * cameras: the `R`, `t` (= centre), `f`, `k` fields of run_sfm's output are read.
+ * cam_stats (nullable): num_cameras x 5 = { #observations, mean distance, median (iround(0.5 n)-th), med80, thresh }
+ * obs_dist  (nullable): one distance per observation in the order of `projections`
+ * outliers / outlier_errors: up to `cap` entries, ordered by (first flagging camera, point index) -- the
+ *   reference lists them by (camera, key index); same set, same errors
+ * global_mean (nullable): the "[RunSFM] Global mean reprojection error" value (:852-856)
+ * Returns the number of outliers (may exceed cap) or a negative error.  Host or device pointers for vmask,
+ * projections, pts.                                                                                          */
+int bsfm_reprojection_outliers(int num_pts, int num_cameras, const char *vmask, const double *projections,
+                               const bsfm_camera_params_t *cams, const bsfm_v3_t *pts, int estimate_distortion,
+                               double min_proj_error_threshold, double max_proj_error_threshold,
+                               const char *pt_protected, double *cam_stats, double *obs_dist,
+                               int32_t *outliers, double *outlier_errors, int cap, double *global_mean);
+
 /* Per-phase device time (ms, CUDA events) of the last solve of this thread:
  * [0] setup (H2D, CSR, Schur structure)  [1] residual/Jacobian/U/V/W  [2] Schur S assembly
  * [3] dense Cholesky + solves  [4] back-substitution/update/function eval  [5] whole solve      */

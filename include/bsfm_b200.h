@@ -40,7 +40,11 @@ int bsfm_set_device(int device);
 
 /* kernel selector for the matcher (env BSFM_MATCH_KERNEL overrides the default):
  *   0 = tcgen05 kind::i8 tensor-core kernel (TMA bulk loads, TMEM accumulators)   [default]
- *   1 = DP4A CUDA-core kernel (cross-check / fallback-free second implementation)            */
+ *   1 = DP4A CUDA-core kernel (independent second implementation used to cross-check; not a fallback)
+ * further switches of kernel 0 (all variants return identical results):
+ *   BSFM_MATCH_EPILOGUE=0  exact chunk-minimum epilogue instead of the bound epilogue (automatic for databases with
+ *                          an image of more than 8192 padded rows)
+ *   BSFM_MATCH_PAIR=1      CTA-pair kernel (tcgen05.mma.cta_group::2, each CTA stages half of every database tile)  */
 #define BSFM_MATCH_KERNEL_TC    0
 #define BSFM_MATCH_KERNEL_DP4A  1
 
@@ -61,8 +65,9 @@ int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double
 /* Device-resident key database for the KeyMatchFull all-pairs loop (src/KeyMatchFull.cpp:93-151).
  * keys  : concatenation of all images' descriptors (sum n_i x 128 bytes), HOST memory
  * key_off: N+1 prefix offsets in keys (units of descriptors)
- * Uploads once, computes squared norms and writes the padded, 128B-swizzled tile layout the
- * tensor-core kernel streams with TMA bulk copies (DESIGN.md "HBM layout").                    */
+ * Uploads once, computes squared norms, sorts the keys of every image by norm and writes the padded,
+ * 128B-swizzled tile layout the tensor-core kernel streams with TMA bulk copies;
+ * results are always reported in the caller's key order.                                      */
 typedef struct bsfm_keydb bsfm_keydb;
 bsfm_keydb *bsfm_keydb_create(const uint8_t *keys, const int64_t *key_off, int num_images);
 /* same, but `keys_dev` already lives in device memory (bench `value` leg; torch data_ptr()) */

@@ -12,6 +12,7 @@
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -155,6 +156,20 @@ struct PhaseTimer {
 
 }  // namespace
 
+// BSFM_BA_HOST_TIMING=1: wall-clock marks of the host path (stderr), to see where an end-to-end call spends its time
+struct HostMarks {
+    bool on = getenv("BSFM_BA_HOST_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ba host] %-28s +%8.3f ms  (%8.3f ms)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
 #define TRY(expr) do { int rc__ = (expr); if (rc__ != BSFM_OK) return rc__; } while (0)
 // PDL launch of a BA kernel on stream `st` (plain launch when BSFM_BA_NO_PDL is set)
 #define BA_LAUNCH(kernel, grid, block, ...)                                                              \
@@ -222,6 +237,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     cudaEvent_t ev_begin = ctx.ev_begin, ev_end = ctx.ev_end;
     BSFM_CUDA_TRY(cudaEventRecord(ev_begin, st));
     g_timing = Timing();
+    HostMarks HM;
 
     DeviceArena D;
     Problem P;
@@ -445,6 +461,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
         BSFM_CUDA_TRY(cudaMemsetAsync(P.dp, 0, (size_t) P.nvars * sizeof(double), st));   // the points' increments stay 0
     }
     PT.end();
+    HM.mark("setup issued");
 
     auto read_scalars = [&]() -> int {
         BSFM_CUDA_TRY(cudaMemcpyAsync(h_sc, P.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
@@ -478,6 +495,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     init_p_eL2 = p_eL2;
     if (!std::isfinite(p_eL2)) stop = 7;
 
+    HM.mark("initial residual");
     for (itno = 0; itno < itmax && !stop; ++itno) {
         PT.begin(1);
         P.camR = d_camR_a;
@@ -586,6 +604,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
         if (p_eL2 <= eps3_sq) stop = 5;    // :1614
     }
     if (itno >= itmax) stop = 3;
+    HM.mark("LM loop");
 
     if (Sout) {
         // export pass (sba_levmar.c:1633-2026): Jacobian at the final p, U/V/W with constraints, UNDAMPED Schur complement
@@ -625,6 +644,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     PT.collect(g_timing.ms);
     g_timing.iterations = itno;
     g_timing.launches = (int) (g_kernel_launches.load() - launches0);
+    HM.mark("copy back + teardown");
     return (stop != 7) ? itno : SBA_ERROR_RC;
 }
 

@@ -21,26 +21,32 @@ const char *last_error() { return g_err; }
 
 int require_device()
 {
+    // the verdict is cached per device: cudaGetDeviceProperties costs a fraction of a millisecond, which is visible in
+    // per-pair MatchKeys calls and in a 10 ms bundle adjustment
+    static std::atomic<int> verified[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev >= 0 && dev < 64 && verified[dev].load(std::memory_order_relaxed) == 1) return BSFM_OK;
     int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
+    e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         set_error("no CUDA device available (%s): libbsfm_b200 has no CPU fallback",
                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
         return BSFM_ERR_NO_DEVICE;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, dev);
+    e = cudaGetDevice(&dev);
+    int major = 0, minor = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
     if (e != cudaSuccess) {
-        set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
         return BSFM_ERR_NO_DEVICE;
     }
-    if (prop.major != 10) {
-        set_error("device %d is sm_%d%d; this library ships sm_100a kernels only", dev, prop.major,
-                  prop.minor);
+    if (major != 10) {
+        set_error("device %d is sm_%d%d; this library ships sm_100a kernels only", dev, major, minor);
         return BSFM_ERR_NO_DEVICE;
     }
+    if (dev >= 0 && dev < 64) verified[dev].store(1, std::memory_order_relaxed);
     return BSFM_OK;
 }
 

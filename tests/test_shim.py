@@ -83,6 +83,22 @@ def test_persistent_keymatchfull_cli_usage():
     assert r.returncode != 0 and "Usage:" in r.stdout and "<list.txt> <outfile> [window_radius]" in r.stdout
 
 
+def test_persistent_keymatchfull_cli_error_paths(tmp_path):
+    """the argument / list-file errors of KeyMatchFull.cpp:25-56,64-90 are reported the same way, before any GPU work"""
+    if not os.path.exists(KMP):
+        pytest.skip("shim/_build/KeyMatchFull_b200_persistent not built")
+    r = subprocess.run([KMP, str(tmp_path / "nope.txt"), str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Error opening file" in r.stdout and "for reading." in r.stdout
+    empty = tmp_path / "empty.txt"
+    empty.write_text("\n   \n")
+    r = subprocess.run([KMP, str(empty), str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode != 0 and "No input files found in" in r.stdout
+    lst = tmp_path / "l.txt"
+    lst.write_text("a.key\n")
+    r = subprocess.run([KMP, str(lst), str(tmp_path / "no_such_dir" / "out.txt")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Could not open" in r.stdout and "for writing." in r.stdout
+
+
 @pytest.mark.gpu
 def test_persistent_keymatchfull_cli_writes_oracle_table(tmp_path, oracle):
     """KeyMatchFull's command line on the persistent matcher -> byte-identical matches.init.txt"""

@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of bundler_sfm_b200 (contract: see the task prompt / DESIGN.md section 6).
 
-Default workload (BASELINE.json configs[1]): synthetic BA, 50 cameras / 20,000 points / 100,000
-observations; one "step" = one full run_sfm-equivalent LM solve.  Metric: LM iterations / second.
-  value : solver called with vmask / measurements / parameters already resident in HBM
-  e2e   : bsfm_run_sfm (the reference-facing C-ABI call) with HOST buffers, H2D/D2H inside the timing
-The same JSON line carries a "match" object: KeyMatchFull config 4 (500 images x 5000 keys, all
-pairs) sharded over the N ranks with an NCCL all-gather of the match table (descriptor-pairs/s).
-`--workload match` makes that the headline line instead.  `--impl reference` times the unmodified
-reference CPU code (oracle/_ref, built from /root/reference) on the host cores.
+Workload selection (`--workload auto`, the default; both arms apply the same rule):
+  1 GPU   -> BA, BASELINE.json configs[2]: 1000 cameras / 500,000 points / 3,000,000 observations (the configuration the
+             metric is quoted on and the one that needs the tensor-core reduced solve); one "step" = one full
+             run_sfm-equivalent LM solve; metric LM iterations / second.  configs[1] (50 / 20k / 100k) rides along as the
+             "ba_config2" object and KeyMatchFull config 4 as the "match" object.
+  N > 1   -> MATCH, BASELINE.json configs[3]: all pairs of 500 images x 5000 SIFT keys sharded over the N ranks with an
+             NCCL all-gather of the match table (the path that shards: `scaling: strong`); BA replicas (configs[1]) ride
+             along as "ba_replicas".
+  value : inputs already resident in HBM when the timed region starts
+  e2e   : the reference-facing C-ABI call (bsfm_run_sfm / keydb create+run+fetch) with HOST buffers, copies inside the timing
+`--workload ba2|ba3|match` forces one.  `--impl reference` times the unmodified reference CPU code (oracle/_ref, built
+from /root/reference) on the host cores this process may use (sched_getaffinity and the cgroup quota).
 """
 import argparse
 import ctypes
@@ -24,8 +28,48 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BA_CFG = dict(num_cameras=50, num_points=20000, views_per_point=5)
+BA_CFGS = {"ba2": dict(num_cameras=50, num_points=20000, views_per_point=5),
+           "ba3": dict(num_cameras=1000, num_points=500000, views_per_point=6)}
+BA_CFG = BA_CFGS["ba2"]
 MATCH_CFG = dict(num_images=500, keys_per_image=5000)
+# the `config.workload` strings are shared by both arms (the driver compares them)
+WORKLOAD_STR = {
+    "ba2": "synthetic BA: 50 cams, 20k points, 100k obs (BASELINE.json configs[1]); one step = one full LM solve",
+    "ba3": "synthetic BA: 1000 cams, 500k points, 3M obs (BASELINE.json configs[2]); one step = one full LM solve",
+    "match": "KeyMatchFull config 4: all pairs of 500 images x 5000 SIFT keys, exact 2-NN + ratio 0.6 (BASELINE.json configs[3])",
+}
+METRIC_STR = {"ba": "LM iterations/s (sparse bundle adjustment solve)", "match": "descriptor-pairs/s (all-pairs SIFT match, KeyMatchFull)"}
+
+
+def usable_cores():
+    """host cores this process may really use: the scheduler affinity mask, capped by the cgroup CPU quota"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except (OSError, ValueError, IndexError):
+            pass
+    return max(1, n)
+
+
+def pick_workload(args):
+    if args.workload in ("ba2", "ba3", "match"):
+        return args.workload
+    if args.workload == "ba":
+        return "ba3"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return "match" if (args.gpus > 1 or world > 1) else "ba3"
 
 
 def load_peaks():

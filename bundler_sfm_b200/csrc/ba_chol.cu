@@ -16,6 +16,7 @@
 // Small systems (<= 1536, e.g. 50 cameras -> 450) are one outer panel: latency-bound by the 450 sequential
 // pivots.  tcgen05 has no fp64 kind; an int8-slice (Ozaki) emulation of the trailing update is future work.
 #include "ba_kernels.cuh"
+#include "ba_chol_large.cuh"
 #include "common.h"
 #include <cstdlib>
 
@@ -459,8 +460,13 @@ __global__ void __launch_bounds__(512) chol_backsolve_blocked_kernel(const doubl
 // symmetric S (both triangles filled by the Schur kernel) + E in row n.  x receives the solution.
 // Lmat: (n+1) x n factor matrix (out of place: A's panel columns stay readable during a step).
 // linv_ws: ceil(n/32) * 1024 doubles (+ n doubles of back-substitution workspace behind it).
-int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *x, Scalars *sc)
+int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *x, Scalars *sc, const TcWorkspace *ws)
 {
+    // systems beyond the latency-bound regime: 256-column panels, tensor-core trailing update (ba_chol_large.cu);
+    // BSFM_BA_CHOL_LARGE_MIN moves the switch-over (tests run the large path on small systems with it)
+    static const int large_min = []() { const char *e = getenv("BSFM_BA_CHOL_LARGE_MIN"); return e ? atoi(e) : 1536; }();
+    static const bool old_large = getenv("BSFM_BA_CHOL_OLD") != nullptr;      // round-1 large path (32-column steps + DMMA), kept for A/B timing
+    if (n > large_min && !old_large) return chol_solve_large(st, A, Lmat, n, linv_ws, linv_ws + (size_t) ((n + NB - 1) / NB) * NB * NB, x, sc, ws);
     const int ld = n, nrows = n + 1;
     const int nbk = (n + NB - 1) / NB;
     double *ywork = linv_ws + (size_t) nbk * NB * NB;

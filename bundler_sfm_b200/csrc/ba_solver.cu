@@ -7,6 +7,7 @@
 // one small scalar block per LM phase.  No CPU fallback.
 #include "common.h"
 #include "ba_kernels.cuh"
+#include "ba_chol_large.cuh"
 #include "../../include/bsfm_b200_ba.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -46,7 +47,7 @@ __global__ void tuple_fill_kernel(int, int, int, const int *, const int *, const
 __global__ void iota_kernel(int *, int);
 __global__ void wout_scatter_kernel(Problem, double *);
 __global__ void vinv_export_kernel(Problem);
-int chol_solve(cudaStream_t, double *, double *, int, double *, double *, Scalars *);
+int chol_solve(cudaStream_t, double *, double *, int, double *, double *, Scalars *, const TcWorkspace *);
 
 __global__ void cam_ptr_kernel(const uint32_t *sorted_cam, int nvis, int m, int *cam_ptr)
 {
@@ -442,7 +443,14 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     P.E = P.S + (size_t) Sdim * Sdim;      // RHS lives in matrix row Sdim (see ba_chol.cu)
     double *d_Lmat;
     TRY(D.alloc(&d_Lmat, ((size_t) Sdim + 1) * Sdim));   // Cholesky factor (out of place)
-    TRY(D.alloc(&d_linv, (size_t) ((Sdim + 31) / 32) * 1024 + (size_t) Sdim + 64)); TRY(D.alloc(&d_da, (size_t) Sdim));
+    TRY(D.alloc(&d_linv, (size_t) ((Sdim + 31) / 32) * 1024 + chol_extra_ws_doubles(Sdim))); TRY(D.alloc(&d_da, (size_t) Sdim));
+    TcWorkspace tcws = {};       // int8 slices of the current panel for the tensor-core trailing update (large systems only)
+    if (!mot && Sdim > 1024 && tc_syrk_available()) {
+        tcws.ns = tc_slices_wanted();
+        TRY(D.alloc(&tcws.slices, tc_slices_bytes(Sdim, tcws.ns)));
+        TRY(D.alloc(&tcws.rscale, (size_t) Sdim + 1));
+        BSFM_CUDA_TRY(cudaMemsetAsync(tcws.slices, 0, tc_slices_bytes(Sdim, tcws.ns), st));
+    }
     const int red_blocks_obs = (nvis + 255) / 256, red_blocks_var = (P.nvars + 255) / 256;
     TRY(D.alloc(&P.partial, (size_t) 3 * std::max(red_blocks_obs, red_blocks_var) + 8));
     const int useg = std::max(1, std::min(32, (nvis / m + 1023) / 1024));   // ~1024 observations per U-accumulation CTA
@@ -534,7 +542,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
             BA_LAUNCH(schur_final_kernel, (nblocks * 32 + 127) / 128, 128, P);
             PT.end();
             PT.begin(3);
-            TRY(chol_solve(st, P.S, d_Lmat, Sdim, d_linv, d_da, P.sc));
+            TRY(chol_solve(st, P.S, d_Lmat, Sdim, d_linv, d_da, P.sc, tcws.slices ? &tcws : nullptr));
             PT.end();
             PT.begin(4);
             BA_LAUNCH(backsub_kernel, (std::max(n, m * cnp) + 127) / 128, 128, P, d_da);
@@ -668,6 +676,66 @@ extern "C" int bsfm_sba_mot_levmar_model(int n, int m, int mcon, const char *vma
 {
     return levmar_impl(1, points, n, m, mcon, vmask, p, cnp, 3, x, covx, mnp, model, jac_mode, itmax, verbose, opts, info,
                        use_constraints, constraints, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// == sba_Axb_Chol, lib/sba-1.5/sba_lapack.c:374-485: x = A^-1 B for symmetric positive definite A (m x m).
+// A, B, x may be host or device pointers; A and B are never modified (the reference overwrites them when
+// iscolmaj == 1; a symmetric matrix reads the same in both orders, so the flag changes nothing else here).
+// Returns 1 on success, 0 when a leading minor is not positive definite (the reference's return values), < 0 on a
+// library error.  `reps` > 1 repeats the factorisation on a fresh copy of A; *ms_out = device time per repetition.
+static int axb_chol_impl(const double *A, const double *B, double *x, int m, int reps, float *ms_out)
+{
+    clear_error();
+    TRY(require_device());
+    if (!A || !B || !x || m <= 0 || reps < 1) { set_error("bsfm_sba_Axb_Chol: bad arguments"); return BSFM_ERR_ARG; }
+    { int dev = 0; BSFM_CUDA_TRY(cudaGetDevice(&dev)); g_pool.bind_device(dev); }
+    DeviceArena D;
+    cudaStream_t st;
+    BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    double *d_src, *d_A, *d_L, *d_linv, *d_x; Scalars *d_sc;
+    const size_t mm = (size_t) m * m;
+    TRY(D.alloc(&d_src, mm + m)); TRY(D.alloc(&d_A, mm + m)); TRY(D.alloc(&d_L, mm + m));
+    TRY(D.alloc(&d_linv, (size_t) ((m + 31) / 32) * 1024 + chol_extra_ws_doubles(m))); TRY(D.alloc(&d_x, (size_t) m)); TRY(D.alloc(&d_sc, 1));
+    TcWorkspace tcws = {};
+    if (m > 1024 && tc_syrk_available()) {
+        tcws.ns = tc_slices_wanted();
+        TRY(D.alloc(&tcws.slices, tc_slices_bytes(m, tcws.ns)));
+        TRY(D.alloc(&tcws.rscale, (size_t) m + 1));
+        BSFM_CUDA_TRY(cudaMemsetAsync(tcws.slices, 0, tc_slices_bytes(m, tcws.ns), st));
+    }
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_src, A, mm * sizeof(double), cudaMemcpyDefault, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_src + mm, B, (size_t) m * sizeof(double), cudaMemcpyDefault, st));
+    BSFM_CUDA_TRY(cudaMemsetAsync(d_sc, 0, sizeof(Scalars), st));
+    cudaEvent_t e0, e1;
+    BSFM_CUDA_TRY(cudaEventCreate(&e0)); BSFM_CUDA_TRY(cudaEventCreate(&e1));
+    float total = 0.f;
+    int rc = BSFM_OK;
+    for (int r = 0; r < reps && rc == BSFM_OK; r++) {
+        cudaMemcpyAsync(d_A, d_src, (mm + m) * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        cudaEventRecord(e0, st);
+        rc = chol_solve(st, d_A, d_L, m, d_linv, d_x, d_sc, tcws.slices ? &tcws : nullptr);
+        cudaEventRecord(e1, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsfm_sba_Axb_Chol: %s", cudaGetErrorString(cudaGetLastError())); rc = BSFM_ERR_CUDA; }
+        float t = 0.f; cudaEventElapsedTime(&t, e0, e1); total += t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != BSFM_OK) return rc;
+    if (ms_out) *ms_out = total / reps;
+    Scalars h;
+    BSFM_CUDA_TRY(cudaMemcpy(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost));
+    if (h.chol_fail) return 0;
+    BSFM_CUDA_TRY(cudaMemcpy(x, d_x, (size_t) m * sizeof(double), cudaMemcpyDefault));
+    return 1;
+}
+extern "C" int bsfm_sba_Axb_Chol(const double *A, const double *B, double *x, int m, int iscolmaj)
+{
+    (void) iscolmaj;
+    return axb_chol_impl(A, B, x, m, 1, nullptr);
+}
+extern "C" int bsfm_sba_Axb_Chol_timed(const double *A, const double *B, double *x, int m, int reps, float *ms_per_solve)
+{
+    return axb_chol_impl(A, B, x, m, reps, ms_per_solve);
 }
 
 extern "C" int bsfm_ba_last_timing(float ms[6], int *iterations, int *launches)

@@ -138,6 +138,26 @@ int bsfm_reprojection_outliers(int num_pts, int num_cameras, const char *vmask, 
                                const char *pt_protected, double *cam_stats, double *obs_dist,
                                int32_t *outliers, double *outlier_errors, int cap, double *global_mean);
 
+/* == sba_Axb_Chol (lib/sba-1.5/sba_lapack.c:374-485, called at sba_levmar.c:1343): x = A^-1 B for a symmetric
+ * positive definite m x m matrix (dpotrf + dpotrs in the reference).  A, B, x: host or device pointers; A and B are
+ * NOT modified (the reference overwrites them when iscolmaj == 1).  Returns 1 on success, 0 when A is not positive
+ * definite -- the reference's own return values -- and a negative BSFM_ERR_* on a library error.
+ * Systems above 1536 unknowns run the 256-column panel factorisation whose trailing update is the tcgen05 int8-slice
+ * kernel (csrc/ba_chol_tc.cu); smaller ones the latency-optimised path (csrc/ba_chol.cu).                          */
+int bsfm_sba_Axb_Chol(const double *A, const double *B, double *x, int m, int iscolmaj);
+/* the same solve repeated `reps` times on a fresh copy of A; *ms_per_solve = mean device time (CUDA events) of one
+ * factorisation + both triangular solves (measurement entry used by bench.py and the tests)                          */
+int bsfm_sba_Axb_Chol_timed(const double *A, const double *B, double *x, int m, int reps, float *ms_per_solve);
+
+/* Per-kernel-class device timing of the large-system Cholesky (systems > 1536 unknowns), for roofline reporting:
+ * bsfm_ba_chol_profile(1) resets the counters of the calling thread and records CUDA events around every launch of
+ * the following solves; bsfm_ba_chol_profile_read returns accumulated ms / launch counts for
+ * [0] diagonal-block factorisation  [1] panel solve (+ int8 slicing)  [2] trailing update  [3] back substitution,
+ * the int8 operations the tensor-core trailing update executed and its fp64-equivalent FLOPs (2 per multiply-add of
+ * the lower triangle).  Call it after the solves have completed.                                                  */
+int bsfm_ba_chol_profile(int enable);
+int bsfm_ba_chol_profile_read(float ms[4], int launches[4], double *tensor_int8_ops, double *fp64_equiv_flops);
+
 /* Per-phase device time (ms, CUDA events) of the last solve of this thread:
  * [0] setup (H2D, CSR, Schur structure)  [1] residual/Jacobian/U/V/W  [2] Schur S assembly
  * [3] dense Cholesky + solves  [4] back-substitution/update/function eval  [5] whole solve      */

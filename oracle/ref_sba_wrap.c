@@ -6,6 +6,9 @@
  *   - ref_hook_sba_motstr_levmar: sfm.c is compiled with -Dsba_motstr_levmar=<this> so the
  *     info[10] vector that run_sfm only prints (sfm.c:872-873) can be read back by tests.
  *   - ref_hook_sba_mot_levmar: the same for the motion-only call (fix_points = 1, sfm.c:843-856).
+ *   - REF_SBA_ITMAX / REF_SBA_EPS5 (environment): cap the iteration count / replace opts[5] that run_sfm hard-codes
+ *     (sfm.c:705-714, :814-815), for equal-iteration-count comparisons and bounded timing samples
+ *     of the big configuration.  The reference sources stay unmodified; only the arguments of the call change.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,11 +30,17 @@ int ref_hook_sba_motstr_levmar(const int n, const int m, const int mcon, char *v
         int use_point_constraints, point_constraints_t *point_constraints,
         double *Vout, double *Sout, double *Uout, double *Wout)
 {
-    int verb = verbose;
+    int verb = verbose, it = itmax;
+    double o[6];      /* run_sfm passes 6 entries; sba_motstr_levmar_x reads opts[5] (sba_levmar.c:610) although SBA_OPTSSZ is 5 */
     const char *q = getenv("REF_SBA_VERBOSE");
     if (q) verb = atoi(q);
+    memcpy(o, opts, 6 * sizeof(double));
+    q = getenv("REF_SBA_ITMAX");
+    if (q) it = atoi(q);
+    q = getenv("REF_SBA_EPS5");
+    if (q) o[5] = atof(q);
     g_last_ret = sba_motstr_levmar(n, m, mcon, vmask, p, cnp, pnp, x, covx, mnp, proj, projac,
-                                   adata, itmax, verb, opts, info, use_constraints, constraints,
+                                   adata, it, verb, o, info, use_constraints, constraints,
                                    use_point_constraints, point_constraints, Vout, Sout, Uout, Wout);
     memcpy(g_last_info, info, sizeof(g_last_info));
     return g_last_ret;

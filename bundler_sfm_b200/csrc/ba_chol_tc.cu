@@ -21,6 +21,9 @@
 #include "ba_chol_large.cuh"
 #include "ba_kernels.cuh"
 #include "tc_ptx.cuh"
+#ifndef BSFM_TCS_DBG
+#define BSFM_TCS_DBG 0
+#endif
 #include "common.h"
 #include <atomic>
 #include <cstdlib>
@@ -218,49 +221,38 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_syrk_kernel(const TcSyrkPar
             double acc[32];
 #pragma unroll
             for (int j = 0; j < 32; j++) acc[j] = 0.0;
-            // Levels are folded in PAIRS (d, d+1): T2 = 256 C_d + C_{d+1} is exact in int64 (< 2^37) and converted once,
-            // which halves the fp64 work per level (the epilogue is bound by the fp64 pipe, not by the tensor pipe);
-            // the odd last level of a K-half is folded alone.
-            for (int half = 0; half < 2; half++) {
-                for (int d = 0; d < ns; d += 2) {
-                    const bool pair = d + 1 < ns;
-                    const double sd = __longlong_as_double((long long) (1023 - 8 * (d + (pair ? 3 : 2))) << 52);
-                    const uint32_t st0 = q & (TCS_STAGES - 1), st1 = (q + 1) & (TCS_STAGES - 1);
-                    TCS_T(e0);
-                    mbar_wait(bar_tfull + 8 * st0, (q >> 2) & 1u);
-                    if (pair) mbar_wait(bar_tfull + 8 * st1, ((q + 1) >> 2) & 1u);
-                    TCS_T(e1);
-                    if (warp == 2 && lane == 0) TCS_ADD(8, e1 - e0);
-                    tc_fence_after();
-                    const uint32_t lane_col = ((uint32_t) (quad * 32) << 16) + ch * 32;
-                    const uint32_t t0 = tmem_base + lane_col + st0 * TC_TILE, t1 = tmem_base + lane_col + st1 * TC_TILE;
-                    uint32_t va[8], vb[8];      // 8 columns at a time: 64 accumulator registers leave room for little else
+            for (int lev = 0; lev < 2 * ns; lev++, q++) {
+                const int d = (lev >= ns) ? lev - ns : lev;
+                const double sd = __longlong_as_double((long long) (1023 - 8 * (d + 2)) << 52);
+                const uint32_t stage = q & (TCS_STAGES - 1);
+                TCS_T(e0);
+                mbar_wait(bar_tfull + 8 * stage, (q >> 2) & 1u);
+                TCS_T(e1);
+                if (warp == 2 && lane == 0) TCS_ADD(8, e1 - e0);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + stage * TC_TILE + ch * 32;
+                uint32_t va[16], vb[16];
+                tmem_ld16(taddr, va);
+                tmem_ld16(taddr + 16, vb);
+                tmem_ld_wait_regs16(va);
+                tmem_ld_wait_regs16(vb);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * stage);     // accumulator stage free again
+#if BSFM_TCS_DBG == 1                      // dev build: no arithmetic (ceiling of the MMA / TMEM side)
+                acc[0] += (double) (va[0] ^ vb[15]);
+#elif BSFM_TCS_DBG == 2                    // dev build: half of the columns only (is the fold arithmetic the bound?)
 #pragma unroll
-                    for (int hc = 0; hc < 4; hc++) {
-                        tmem_ld8(t0 + 8 * hc, va);
-                        if (pair) tmem_ld8(t1 + 8 * hc, vb);
-                        tmem_ld_wait_regs8(va);
-                        if (pair) tmem_ld_wait_regs8(vb);
-                        if (hc == 3) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) { mbar_arrive(bar_tempty + 8 * st0); if (pair) mbar_arrive(bar_tempty + 8 * st1); }
-                        }
-                        if (pair) {
+                for (int j = 0; j < 16; j++) acc[j] = fma(i2d(va[j]), sd, acc[j]);
+                acc[16] += (double) vb[3];
+#else
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const long long t2 = (long long) (int) va[j] * 256 + (long long) (int) vb[j];
-                                acc[8 * hc + j] = fma(ll2d(t2), sd, acc[8 * hc + j]);
-                            }
-                        } else {
+                for (int j = 0; j < 16; j++) acc[j] = fma(i2d(va[j]), sd, acc[j]);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) acc[8 * hc + j] = fma(i2d(va[j]), sd, acc[8 * hc + j]);
-                        }
-                    }
-                    q += pair ? 2 : 1;
-                    TCS_T(e2);
-                    if (warp == 2 && lane == 0) TCS_ADD(9, e2 - e1);
-                }
+                for (int j = 0; j < 16; j++) acc[16 + j] = fma(i2d(vb[j]), sd, acc[16 + j]);
+#endif
+                TCS_T(e2);
+                if (warp == 2 && lane == 0) TCS_ADD(9, e2 - e1);
             }
             TCS_T(w0);
             // The MMA's M side is the COLUMN tile: thread = matrix column, register j = matrix row, so that for every j

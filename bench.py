@@ -160,7 +160,7 @@ def _ref_ba_worker(args):
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from bundler_sfm_b200 import synth
     from oracle import loader
-    scene = synth.ba_scene(seed=seed, **BA_CFG)
+    scene = synth.ba_scene(seed=seed, **BA_CFGS["ba2"])
     its = 0
     t0 = time.perf_counter()
     for _ in range(nsolves):
@@ -169,7 +169,7 @@ def _ref_ba_worker(args):
     return its, time.perf_counter() - t0
 
 
-def run_reference_ba(steps, warmup, procs):
+def run_reference_ba2(steps, warmup, procs):
     """`procs` independent reference processes (the reference is single-threaded and not re-entrant,
     SURVEY.md F6), each solving the config-2 scene `steps` times: aggregate LM iterations / s."""
     import multiprocessing as mp
@@ -184,6 +184,26 @@ def run_reference_ba(steps, warmup, procs):
         wall = time.perf_counter() - t0
     its = sum(r[0] for r in res)
     return its / wall, wall, kind, its
+
+
+def run_reference_ba3(lm_iterations, threads, scene=None):
+    """The reference on config 3 is ONE process (sba is single-threaded; only dpotrf runs on `threads` OpenBLAS
+    threads): a bounded sample = the unmodified run_sfm stopped after `lm_iterations` LM iterations (REF_SBA_ITMAX
+    changes the itmax argument of the call, nothing in the reference).  -> (LM it/s, seconds, kind, iterations)"""
+    os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
+    os.environ["REF_SBA_ITMAX"] = str(lm_iterations)
+    from bundler_sfm_b200 import synth
+    from oracle import loader
+    if loader.ref_sba() is None:
+        return None
+    if scene is None:
+        scene = synth.ba_scene(seed=1234, **BA_CFGS["ba3"])
+    t0 = time.perf_counter()
+    out = loader.run_sfm_ref(scene)
+    dt = time.perf_counter() - t0
+    os.environ.pop("REF_SBA_ITMAX")
+    its = int(out["info"][5])
+    return its / dt, dt, "reference", its
 
 
 def _ref_match_worker(args):
@@ -201,12 +221,13 @@ def _ref_match_worker(args):
     return npairs, time.perf_counter() - t0
 
 
-def run_reference_match(pairs_per_proc, procs):
+def run_reference_match(pairs_per_proc, procs, warmup=1):
     import multiprocessing as mp
     kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_match.so")) else "port"
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
-        pool.map(_ref_match_worker, [(7 + r, 1) for r in range(procs)])
+        if warmup > 0:
+            pool.map(_ref_match_worker, [(7 + r, 1) for r in range(procs)])
         t0 = time.perf_counter()
         res = pool.map(_ref_match_worker, [(7 + r, pairs_per_proc) for r in range(procs)])
         wall = time.perf_counter() - t0
@@ -219,27 +240,47 @@ def main_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
-    if args.workload == "match":
-        pairs_per_proc = max(1, min(args.steps, 40))
-        dps, ips, wall, kind, npairs = run_reference_match(pairs_per_proc, procs)
-        line = {"impl": "reference", "metric": "descriptor-pairs/s (all-pairs SIFT match, KeyMatchFull)", "value": dps, "unit": "descriptor-pairs/s",
-                "n_gpus": args.gpus, "steps": pairs_per_proc, "warmup": 1, "ms_per_step": 1e3 * wall / pairs_per_proc, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "KeyMatchFull config 4: 500 images x 5000 SIFT keys (bounded sample of image pairs)", **MATCH_CFG},
+    procs = usable_cores()
+    wl = pick_workload(args)
+    if wl == "match":
+        # one step = `pairs` image pairs per process (one process per usable core); the run is sized to ~1-2 minutes
+        pairs = 4
+        steps = max(1, min(args.steps, 6))
+        dps, ips, wall, kind, npairs = run_reference_match(pairs * steps, procs, warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC_STR["match"], "value": dps, "unit": "descriptor-pairs/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WORKLOAD_STR["match"], **MATCH_CFG},
                 "cpu_baseline": {"value": dps, "unit": "descriptor-pairs/s", "cores": procs, "kind": kind,
-                                 "sample": f"{npairs} image pairs of 5000x5000 keys, stock ANN kd-tree priority search (200-visit cap), one process per core"},
+                                 "sample": f"{npairs} image pairs of 5000x5000 keys ({pairs} per process and step), stock ANN kd-tree priority search "
+                                           f"(200-visit cap, the reference's default), one single-threaded process per usable core"},
                 "e2e": {"value": dps, "unit": "descriptor-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "image_pairs_per_s": ips}
+    elif wl == "ba3":
+        # 835 s for the full solve (tests/golden/ba_config3_ref.json): a step = the same solve stopped after 2 LM iterations
+        res = run_reference_ba3(2, procs)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_sba.so not built (needs /root/reference at build time)"}), flush=True)
+            return
+        ips, wall, kind, its = res
+        line = {"impl": "reference", "metric": METRIC_STR["ba"], "value": ips, "unit": "LM iterations/s",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * wall, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD_STR["ba3"], **BA_CFGS["ba3"]},
+                "cpu_baseline": {"value": ips, "unit": "LM iterations/s", "cores": procs, "kind": kind,
+                                 "sample": f"one run_sfm call of the unmodified reference stopped after {its} LM iterations ({wall:.1f} s incl. the initial "
+                                           f"error evaluation); sba is single-threaded, dpotrf uses {procs} OpenBLAS threads; the full 20-iteration solve took "
+                                           f"835 s in the build container (tests/golden/ba_config3_ref.json)"},
+                "e2e": {"value": ips, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     else:
         steps = max(1, min(args.steps, 3))
-        ips, wall, kind, its = run_reference_ba(steps, min(args.warmup, 1), procs)
-        line = {"impl": "reference", "metric": "LM iterations/s (sparse bundle adjustment solve)", "value": ips, "unit": "LM iterations/s",
+        ips, wall, kind, its = run_reference_ba2(steps, min(args.warmup, 1), procs)
+        line = {"impl": "reference", "metric": METRIC_STR["ba"], "value": ips, "unit": "LM iterations/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic BA: 50 cams, 20k points, 100k obs (BASELINE.json configs[1])", **BA_CFG},
+                "config": {"workload": WORKLOAD_STR["ba2"], **BA_CFGS["ba2"]},
                 "cpu_baseline": {"value": ips, "unit": "LM iterations/s", "cores": procs, "kind": kind,
-                                 "sample": f"{steps} full run_sfm solves per process, {procs} independent single-threaded processes (one per host core)"},
+                                 "sample": f"{steps} full run_sfm solves per process, {procs} independent single-threaded processes (one per usable core)"},
                 "e2e": {"value": ips, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -261,10 +302,12 @@ def flush_l2(torch, buf):
     buf.add_(1)   # 512 MB read+write > 126 MB L2
 
 
-def bench_ba(args, torch, dist, rank, world, dev):
+def bench_ba(args, torch, dist, rank, world, dev, cfg_key, steps, warmup, scene=None):
     from bundler_sfm_b200 import bundle, synth
     os.environ.setdefault("BSFM_BA_VERBOSE", "0")
-    scene = synth.ba_scene(seed=1234 + rank, **BA_CFG)
+    cfg = BA_CFGS[cfg_key]
+    if scene is None:
+        scene = synth.ba_scene(seed=1234 + rank, **cfg)
     n, m = scene["vmask"].shape
     nvis = scene["projections"].shape[0]
     p0, cnp = bundle.pack_params(scene)
@@ -297,7 +340,7 @@ def bench_ba(args, torch, dist, rank, world, dev):
     saved = os.dup(1)
     os.dup2(devnull, 1)
     try:
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             solve_resident(); solve_e2e()
         lib = bundle.load_library()
         launches0 = lib.bsfm_kernel_launches()
@@ -306,8 +349,7 @@ def bench_ba(args, torch, dist, rank, world, dev):
         torch.cuda.synchronize()
         sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
         its_sum, dev_ms, wall = 0, 0.0, 0.0
-        phase = np.zeros(6)
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush_l2(torch, flush)
             its, w, tm = solve_resident()
             its_sum += its; wall += w; dev_ms += tm["total_ms"]
@@ -316,15 +358,20 @@ def bench_ba(args, torch, dist, rank, world, dev):
         if dist is not None:
             dist.barrier()
         e_its, e_wall = 0, 0.0
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush_l2(torch, flush)
             its, w, out = solve_e2e()
             e_its += its; e_wall += w
         torch.cuda.synchronize()
         clocks = sampler.stop()
+        # one more solve with per-phase events and (large systems) per-kernel-class events of the dense Cholesky
         os.environ["BSFM_BA_TIMING"] = "1"
+        lib.bsfm_ba_chol_profile(1)
         _, _, tm = solve_resident()
         os.environ.pop("BSFM_BA_TIMING")
+        pms = (ctypes.c_float * 4)(); pl = (ctypes.c_int * 4)(); ops = ctypes.c_double(); fl = ctypes.c_double()
+        lib.bsfm_ba_chol_profile_read(pms, pl, ctypes.byref(ops), ctypes.byref(fl))
+        lib.bsfm_ba_chol_profile(0)
     finally:
         os.dup2(saved, 1)
         os.close(saved)
@@ -342,12 +389,21 @@ def bench_ba(args, torch, dist, rank, world, dev):
     # algorithmic HBM bytes per LM iteration (SURVEY.md 8d / DESIGN.md): ~0.7 KB per observation + 16 (9m)^2
     alg_bytes = 0.7e3 * nvis + 16.0 * (9 * m) ** 2
     iters_one = tm["iterations"]
-    return {
-        "value": its_all / dev_s, "ms_per_step": 1e3 * dev_s / args.steps, "e2e_value": e_its_all / e_s,
+    res = {
+        "value": its_all / dev_s, "ms_per_step": 1e3 * dev_s / steps, "e2e_value": e_its_all / e_s,
         "h2d": h2d, "d2h": d2h, "launches": int(launches), "clocks": clocks, "rmse": rmse, "iterations_per_solve": iters_one,
         "phase_ms": {k: v for k, v in tm.items()},
         "roofline_achieved_gbs": alg_bytes * iters_one / (tm["total_ms"] * 1e-3) / 1e9,
+        "steps": steps, "warmup": warmup,
     }
+    if pl[2] > 0 and pms[2] > 0:      # large system: the tensor-core trailing update is the dominant kernel
+        res["chol"] = {
+            "kernel_ms_one_solve": {"diag_block": pms[0], "panel_solve": pms[1], "trailing_update_tcgen05": pms[2], "back_substitution": pms[3]},
+            "launches_one_solve": {"diag_block": pl[0], "panel_solve": pl[1], "trailing_update_tcgen05": pl[2], "back_substitution": pl[3]},
+            "trailing_int8_tops": ops.value / (pms[2] * 1e-3) / 1e12, "trailing_fp64_equiv_tflops": fl.value / (pms[2] * 1e-3) / 1e12,
+            "trailing_avg_launch_ms": pms[2] / pl[2], "int8_ops_per_launch": ops.value / pl[2],
+        }
+    return res
 
 
 def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image, steps, warmup):
@@ -417,20 +473,35 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
             "wall_ms_per_pass": 1e3 * wall / steps, "launches": int(launches), "clocks": clocks,
             "search_kernel_ms_per_pass_max_rank": 1e3 * search_s / steps, "int8_tops_search_kernel": dp * 256 / world / (search_s / steps) / 1e12,
             "e2e_desc_pairs_per_s": dp / e2e_wall, "matches": int(total_matches), "h2d_bytes": int(keys.nbytes), "images": num_images, "keys_per_image": keys_per_image,
-            "pairs": npairs, "shard": [int(b), int(e)]}
+            "pairs": npairs, "shard": [int(b), int(e)], "steps": steps, "warmup": warmup}
 
 
-def cpu_baseline_ba():
+def cpu_baseline_ba2():
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from bundler_sfm_b200 import synth
     from oracle import loader
-    scene = synth.ba_scene(seed=1234, **BA_CFG)
+    scene = synth.ba_scene(seed=1234, **BA_CFGS["ba2"])
     t0 = time.perf_counter()
     out = loader.run_sfm_oracle(scene)
     dt = time.perf_counter() - t0
     kind = "reference" if loader.ref_sba() is not None else "port"
     return {"value": out["info"][5] / dt, "unit": "LM iterations/s", "cores": 1, "kind": kind,
             "sample": f"one full run_sfm solve of the config ({int(out['info'][5])} LM iterations, {dt:.1f} s), single thread"}
+
+
+def cpu_baseline_ba3(scene):
+    """bounded live sample of the reference on config 3: run_sfm stopped after ONE LM iteration (~40-60 s)"""
+    cores = usable_cores()
+    res = run_reference_ba3(1, cores, scene)
+    if res is None:
+        stored = json.load(open(os.path.join(ROOT, "tests", "golden", "ba_config3_ref.json")))
+        return {"value": stored["info"][5] / stored["seconds"], "unit": "LM iterations/s", "cores": 8, "kind": "reference",
+                "sample": "oracle/_ref not available on this box: stored summary of the full reference solve in the build container "
+                          "(tests/golden/ba_config3_ref.json: 20 LM iterations in 835 s, 8 OpenBLAS threads for dpotrf)"}
+    ips, dt, kind, its = res
+    return {"value": ips, "unit": "LM iterations/s", "cores": cores, "kind": kind,
+            "sample": f"the unmodified run_sfm on this scene stopped after {its} LM iteration(s): {dt:.1f} s incl. the initial error evaluation "
+                      f"(sba single-threaded, dpotrf on {cores} OpenBLAS threads); stored full solve: 20 iterations in 835 s (tests/golden/ba_config3_ref.json)"}
 
 
 def cpu_baseline_match(budget_s=12.0):
@@ -461,9 +532,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ba", choices=["ba", "match"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "ba", "ba2", "ba3", "match"])
     ap.add_argument("--match-images", type=int, default=MATCH_CFG["num_images"])
-    ap.add_argument("--no-match", action="store_true", help="skip the MATCH sub-benchmark")
+    ap.add_argument("--no-side", action="store_true", help="skip the side objects (ba_config2 / match / ba_replicas)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -478,58 +549,81 @@ def main():
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
-    warm = max(args.warmup, 3)
-    args.warmup = warm
+    args.warmup = max(args.warmup, 3)
     peaks = load_peaks()
+    wl = pick_workload(args)
+    i8_peak = 2.0 * peaks["bf16_tflops"]
 
-    ba = bench_ba(args, torch, dist, rank, world, dev) if args.workload == "ba" else None
-    match = None
-    if not args.no_match or args.workload == "match":
-        match = bench_match(args, torch, dist, rank, world, dev, args.match_images, MATCH_CFG["keys_per_image"],
-                            steps=max(1, min(args.steps, 3)), warmup=1)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_ba() if args.workload == "ba" else cpu_baseline_match()
-
-    if rank == 0:
-        i8_peak = 2.0 * peaks["bf16_tflops"]
-        if args.workload == "ba":
-            line = {
-                "metric": "LM iterations/s (sparse bundle adjustment solve)", "value": ba["value"], "unit": "LM iterations/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ba["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic BA: 50 cams, 20k points, 100k obs (BASELINE.json configs[1]); one step = one full LM solve; "
-                                       "N>1 = N independent replicas (BA does not shard); L2 flushed between timed steps (256 MB buffer)",
-                           **BA_CFG, "jacobian": "finite-difference (reference-compatible)", "lm_iterations_per_solve": ba["iterations_per_solve"],
-                           "final_rmse_px": ba["rmse"]},
-                "e2e": {"value": ba["e2e_value"], "unit": "LM iterations/s", "h2d_bytes_per_step": ba["h2d"], "d2h_bytes_per_step": ba["d2h"]},
-                "gpu_launches": ba["launches"], "clocks": ba["clocks"],
-                "roofline": {"bound": "hbm", "achieved": ba["roofline_achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": ba["roofline_achieved_gbs"] / peaks["hbm_gbs"], "traffic": None,
-                             "note": "whole LM iteration: algorithmic bytes 0.7 KB/obs + 16(9m)^2 per iteration / device time; latency-bound at this size; peak " + peaks["source"]},
-                "ba_phase_ms_one_solve": ba["phase_ms"],
-            }
+    def ba_object(ba, key):
+        """the BA fields of a JSON line (headline or side object)"""
+        obj = {"metric": METRIC_STR["ba"], "value": ba["value"], "unit": "LM iterations/s", "steps": ba["steps"], "warmup": ba["warmup"],
+               "ms_per_step": ba["ms_per_step"], "dtype": "f64",
+               "config": {"workload": WORKLOAD_STR[key] + "; N>1 = N independent replicas (BA does not shard); L2 flushed between timed steps (256 MB buffer)",
+                          **BA_CFGS[key], "jacobian": "finite-difference (reference-compatible)", "lm_iterations_per_solve": ba["iterations_per_solve"],
+                          "final_rmse_px": ba["rmse"]},
+               "e2e": {"value": ba["e2e_value"], "unit": "LM iterations/s", "h2d_bytes_per_step": ba["h2d"], "d2h_bytes_per_step": ba["d2h"]},
+               "gpu_launches": ba["launches"], "clocks": ba["clocks"], "ba_phase_ms_one_solve": ba["phase_ms"]}
+        if "chol" in ba:
+            c = ba["chol"]
+            obj["roofline"] = {"bound": "tensor", "achieved": c["trailing_int8_tops"], "peak": i8_peak, "unit": "TOP/s (int8)",
+                               "frac": c["trailing_int8_tops"] / i8_peak, "traffic": None,
+                               "kernel": "tc_syrk_kernel (tcgen05 kind::i8 int8-slice trailing update of the reduced-camera Cholesky)",
+                               "fp64_equivalent_tflops": c["trailing_fp64_equiv_tflops"],
+                               "note": "dominant kernel of the solve; achieved = algorithmic int8 ops (28 slice products x 2 x lower-triangle MACs) / CUDA-event "
+                                       "time of its launches in one solve; peak = 2 x bf16 dense, " + peaks["source"]}
+            obj["cholesky_kernels"] = c
         else:
-            line = {
-                "metric": "descriptor-pairs/s (all-pairs SIFT match, KeyMatchFull)", "value": match["desc_pairs_per_s"], "unit": "descriptor-pairs/s",
-                "n_gpus": world, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": match["ms_per_pass"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "KeyMatchFull config 4: all pairs of 500 images x 5000 SIFT keys, exact 2-NN + ratio 0.6; descriptors (320 MB) exceed L2",
-                           **MATCH_CFG},
-                "e2e": {"value": match["e2e_desc_pairs_per_s"], "unit": "descriptor-pairs/s", "h2d_bytes_per_step": match["h2d_bytes"], "d2h_bytes_per_step": match["matches"] * 8},
+            obj["roofline"] = {"bound": "hbm", "achieved": ba["roofline_achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": ba["roofline_achieved_gbs"] / peaks["hbm_gbs"], "traffic": None,
+                               "note": "whole LM iteration: algorithmic bytes 0.7 KB/obs + 16(9m)^2 per iteration / device time; latency-bound at this size; peak " + peaks["source"]}
+        return obj
+
+    def match_object(match):
+        return {"metric": METRIC_STR["match"], "value": match["desc_pairs_per_s"], "unit": "descriptor-pairs/s",
+                "steps": match["steps"], "warmup": match["warmup"], "ms_per_step": match["ms_per_pass"], "dtype": "u8",
+                "config": {"workload": WORKLOAD_STR["match"] + "; descriptors (320 MB) exceed L2", **MATCH_CFG},
+                "e2e": {"value": match["e2e_desc_pairs_per_s"], "unit": "descriptor-pairs/s", "h2d_bytes_per_step": match["h2d_bytes"],
+                        "d2h_bytes_per_step": match["matches"] * 8},
                 "gpu_launches": match["launches"], "clocks": match["clocks"],
                 "roofline": {"bound": "tensor", "achieved": match["int8_tops_search_kernel"], "peak": i8_peak, "unit": "TOP/s (int8)",
                              "frac": match["int8_tops_search_kernel"] / i8_peak, "traffic": None,
-                             "note": "tcgen05 kind::i8 search kernel; 256 int8 ops per descriptor pair; peak = 2 x bf16 dense, " + peaks["source"]},
-            }
-        if match is not None:
-            match["roofline"] = {"bound": "tensor", "achieved": match["int8_tops_search_kernel"], "peak": i8_peak, "unit": "TOP/s (int8)",
-                                 "frac": match["int8_tops_search_kernel"] / i8_peak,
-                                 "note": "search kernel per GPU; peak = 2 x bf16 dense " + peaks["source"]}
-            line["match"] = match
+                             "note": "tcgen05 kind::i8 search kernel per GPU; 256 int8 ops per descriptor pair; peak = 2 x bf16 dense, " + peaks["source"]},
+                "match_detail": match}
+
+    line, cpu = None, None
+    if wl in ("ba2", "ba3"):
+        from bundler_sfm_b200 import synth
+        scene = synth.ba_scene(seed=1234 + rank, **BA_CFGS[wl])
+        ba = bench_ba(args, torch, dist, rank, world, dev, wl, steps=args.steps, warmup=args.warmup, scene=scene)
+        line = {"n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", **ba_object(ba, wl)}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_ba3(scene) if wl == "ba3" else cpu_baseline_ba2()
+        del scene
+        if not args.no_side:
+            if wl == "ba3":
+                side = bench_ba(args, torch, dist, rank, world, dev, "ba2", steps=min(args.steps, 10), warmup=3)
+                line["ba_config2"] = ba_object(side, "ba2")
+                if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                    line["ba_config2"]["cpu_baseline"] = cpu_baseline_ba2()
+            m = bench_match(args, torch, dist, rank, world, dev, args.match_images, MATCH_CFG["keys_per_image"], steps=max(1, min(args.steps, 3)), warmup=1)
+            line["match"] = match_object(m)
+    else:
+        m = bench_match(args, torch, dist, rank, world, dev, args.match_images, MATCH_CFG["keys_per_image"], steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)))
+        line = {"n_gpus": world, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic", **match_object(m)}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_match()
+        if not args.no_side:
+            side = bench_ba(args, torch, dist, rank, world, dev, "ba2", steps=min(args.steps, 10), warmup=3)
+            line["ba_replicas"] = {"scaling": "weak", **ba_object(side, "ba2")}
+
+    if rank == 0:
+        # key order of the contract first
+        head = {k: line[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                                     "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline")}
+        head.update({k: v for k, v in line.items() if k not in head})
         if cpu is not None:
-            line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+            head["cpu_baseline"] = cpu
+        print(json.dumps(head), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -177,8 +177,32 @@ def pack_params(scene, est_focal_length=1, undistort=1, f_scale=0.001, k_scale=5
     return np.concatenate([a.reshape(-1), np.asarray(scene["pts"], float).reshape(-1)]), cnp
 
 
+def unpack_params(p, scene, est_focal_length=1, undistort=1, f_scale=0.001, k_scale=5.0):
+    """run_sfm's unpacking (lib/sfm-driver/sfm.c:876-929) in numpy: p -> dict(R, c, f, k, pts); R = exp([w]x) R_init"""
+    m, n = len(scene["f"]), scene["pts"].shape[0]
+    cnp = 6 + (1 if est_focal_length else 0) + (2 if undistort else 0)
+    a = np.asarray(p[:m * cnp], float).reshape(m, cnp)
+    R0 = np.asarray(scene["R"], float).reshape(m, 3, 3)
+    R = np.empty_like(R0)
+    for j in range(m):
+        w = a[j, 3:6]
+        th = np.sqrt((w * w).sum())
+        if th == 0.0:
+            R[j] = R0[j]
+            continue
+        nx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) / th
+        R[j] = (np.eye(3) + nx * np.sin(th) + nx @ nx * (1.0 - np.cos(th))) @ R0[j]
+    c = 6
+    f = np.asarray(scene["f"], float).copy()
+    if est_focal_length:
+        f = a[:, 6] / f_scale
+        c = 7
+    k = a[:, c:c + 2] / k_scale if undistort else np.zeros((m, 2))
+    return {"R": R.reshape(m, 9), "c": a[:, 0:3].copy(), "f": f, "k": k, "pts": np.asarray(p[m * cnp:], float).reshape(n, 3).copy()}
+
+
 def levmar_model(n, m, vmask_ptr, p_ptr, x_ptr, cnp, R_init, f_fixed, est_focal_length=1, undistort=1,
-                 explicit_camera_centers=1, eps2=1e-12, itmax=150, verbose=0, jac_mode=0):
+                 explicit_camera_centers=1, eps2=1e-12, itmax=150, verbose=0, jac_mode=0, eps5=4.0e-2):
     """bsfm_sba_motstr_levmar_model with raw (host or DEVICE) pointers for vmask / p / x.
     Returns (iterations, info[10])."""
     lib = load_library()
@@ -191,7 +215,7 @@ def levmar_model(n, m, vmask_ptr, p_ptr, x_ptr, cnp, R_init, f_fixed, est_focal_
     R_init = np.ascontiguousarray(R_init, dtype=np.float64)
     f_fixed = np.ascontiguousarray(f_fixed, dtype=np.float64)
     model = SfmModel(est_focal_length, undistort, explicit_camera_centers, 0.001, 5.0, R_init.ctypes.data, f_fixed.ctypes.data)
-    opts = np.array([1.0e-3, 1.0e-10, eps2, 1.0e-12, 0.0, 4.0e-2])     # sfm.c:705-714
+    opts = np.array([1.0e-3, 1.0e-10, eps2, 1.0e-12, 0.0, eps5])     # sfm.c:705-714 (opts[5] = 4e-2 there)
     info = np.zeros(10)
     rc = fn(n, m, 0, vmask_ptr, p_ptr, cnp, 3, x_ptr, None, 2, ctypes.addressof(model), jac_mode, itmax, verbose,
             opts.ctypes.data, info.ctypes.data, 0, None, 0, None, None, None, None, None)

@@ -490,6 +490,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     double mu = 0.0, eab_inf = 0.0, p_eL2, pdp_eL2, p_L2 = 0.0, dp_L2 = DBL_MAX, dF, dL, init_p_eL2, max_diag = DBL_MIN, pen = 0.0;
     int nu = 2, nu2, stop = 0, nfev = 0, njev = 0, nlss = 0, itno = 0;
     const bool any_constraints = use_constraints || use_point_constraints;
+    bool almost_singular = false;
     const bool s_dense = (int64_t) nblocks == (int64_t) (m - mcon) * (m - mcon + 1) / 2;   // every block written by the Schur pass
 
     PT.begin(4);
@@ -565,7 +566,10 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
                         fprintf(stderr, "SBA: the matrix of the augmented normal equations is almost singular in %s(),\n"
                                         "     minimization should be restarted from the current solution with an increased damping term\n", fname);
                         set_error("augmented normal equations almost singular");
-                        return SBA_ERROR_RC;
+                        // the reference leaves through freemem_and_return with the last ACCEPTED p in place (it updates p
+                        // in place on every accepted step, sba_levmar.c:1456-1462): fall through to the common tail
+                        almost_singular = true;
+                        break;
                     }
                     ++nfev;
                     pdp_eL2 = h_sc->e_L2;
@@ -599,6 +603,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
                 }
             }
             if (!take_moredamping) break;
+            if (almost_singular) break;
             // moredamping :1584-1597
             mu *= nu;
             nu2 = nu << 1;
@@ -609,6 +614,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
             }
             nu = nu2;
         }
+        if (almost_singular) break;
         if (p_eL2 <= eps3_sq) stop = 5;    // :1614
     }
     if (itno >= itmax) stop = 3;
@@ -653,7 +659,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     g_timing.iterations = itno;
     g_timing.launches = (int) (g_kernel_launches.load() - launches0);
     HM.mark("copy back + teardown");
-    return (stop != 7) ? itno : SBA_ERROR_RC;
+    return (stop != 7 && !almost_singular) ? itno : SBA_ERROR_RC;
 }
 
 extern "C" int bsfm_sba_motstr_levmar_model(int n, int m, int mcon, const char *vmask, double *p, int cnp, int pnp,
@@ -851,7 +857,10 @@ extern "C" int bsfm_run_sfm(int num_pts, int num_cameras, int ncons, char *vmask
                                           use_constraints, use_constraints ? constraints.data() : nullptr,
                                           use_point_constraints, use_point_constraints ? point_constraints.data() : nullptr,
                                           Vout, Sout, Uout, Wout);
-    if (rc < -1) return rc;     // BSFM_ERR_*: nothing was solved, leave the caller's data untouched
+    if (rc < -1) {              // BSFM_ERR_*: nothing was solved; the caller's cameras get their scale fields back (they were set
+        for (int j = 0; j < num_cameras; j++) { init_camera_params[j].f_scale = 1.0; init_camera_params[j].k_scale = 1.0; }   // to 0.001 / 5 above)
+        return rc;
+    }
     printf("[run_sfm] Number of iterations: %d\n", (int) info[5]);   // sfm.c:872-873
     printf("info[6] = %0.3f\n", info[6]);
     if (info_out) memcpy(info_out, info, sizeof info);

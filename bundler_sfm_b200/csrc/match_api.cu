@@ -6,7 +6,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 #include <algorithm>
+#include <atomic>
 #include <climits>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -108,12 +110,20 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
     const int64_t total_keys = key_off[N];
     uint8_t *d_raw = nullptr;
     int64_t *d_key_off = nullptr;
+    // temporaries are released on every exit path (an early BSFM_CUDA_TRY return used to leak them)
+    struct Temps {
+        std::vector<void *> ptrs;
+        ~Temps() { for (void *q : ptrs) cudaFree(q); }
+        void own(void *q) { if (q) ptrs.push_back(q); }
+    } temps;
     BSFM_CUDA_TRY(cudaMalloc(&d_key_off, (size_t) (N + 1) * sizeof(int64_t)));
+    temps.own(d_key_off);
     BSFM_CUDA_TRY(cudaMemcpyAsync(d_key_off, key_off, (size_t) (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, db->stream));
     if (keys_on_device) {
         d_raw = const_cast<uint8_t *>(keys);
     } else if (total_keys > 0) {
         BSFM_CUDA_TRY(cudaMalloc(&d_raw, (size_t) total_keys * DESC_BYTES));
+        temps.own(d_raw);
         BSFM_CUDA_TRY(cudaMemcpyAsync(d_raw, keys, (size_t) total_keys * DESC_BYTES, cudaMemcpyHostToDevice, db->stream));
     }
     // per-image stable sort of the keys by squared norm (the tensor-core epilogue relies on norm-sorted chunks)
@@ -121,9 +131,11 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
     void *d_tmp = nullptr;
     if (total_keys > (int64_t) INT_MAX - 1) { set_error("bsfm_keydb_create: more than 2^31 keys"); return BSFM_ERR_ARG; }
     const size_t nk = (size_t) std::max<int64_t>(total_keys, 1);
-    BSFM_CUDA_TRY(cudaMalloc(&d_nraw, nk * 4)); BSFM_CUDA_TRY(cudaMalloc(&d_nsorted, nk * 4));
-    BSFM_CUDA_TRY(cudaMalloc(&d_iota, nk * 4)); BSFM_CUDA_TRY(cudaMalloc(&d_src, nk * 4));
-    BSFM_CUDA_TRY(cudaMalloc(&d_seg, (size_t) (N + 1) * 4));
+    BSFM_CUDA_TRY(cudaMalloc(&d_nraw, nk * 4)); temps.own(d_nraw);
+    BSFM_CUDA_TRY(cudaMalloc(&d_nsorted, nk * 4)); temps.own(d_nsorted);
+    BSFM_CUDA_TRY(cudaMalloc(&d_iota, nk * 4)); temps.own(d_iota);
+    BSFM_CUDA_TRY(cudaMalloc(&d_src, nk * 4)); temps.own(d_src);
+    BSFM_CUDA_TRY(cudaMalloc(&d_seg, (size_t) (N + 1) * 4)); temps.own(d_seg);
     if (total_keys > 0) {
         std::vector<int32_t> seg((size_t) N + 1);
         for (int i = 0; i <= N; i++) seg[(size_t) i] = (int32_t) key_off[i];
@@ -133,6 +145,7 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
         size_t tb = 0;
         cub::DeviceSegmentedSort::StableSortPairs(nullptr, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, N, d_seg, d_seg + 1, db->stream);
         BSFM_CUDA_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tb, 1)));
+        temps.own(d_tmp);
         cub::DeviceSegmentedSort::StableSortPairs(d_tmp, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, N, d_seg, d_seg + 1, db->stream);
         count_launch(3);
         BSFM_CUDA_TRY(cudaGetLastError());
@@ -146,8 +159,6 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
         BSFM_KERNEL_CHECK();
     }
     BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
-    if (!keys_on_device && d_raw) cudaFree(d_raw);
-    cudaFree(d_key_off); cudaFree(d_nraw); cudaFree(d_nsorted); cudaFree(d_iota); cudaFree(d_src); cudaFree(d_seg); cudaFree(d_tmp);
     return BSFM_OK;
 }
 
@@ -232,6 +243,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     const int K = (int) run.size();
     RunImage *d_run = nullptr;
     BSFM_CUDA_TRY(cudaMalloc(&d_run, (size_t) K * sizeof(RunImage)));
+    struct RunGuard { RunImage *&q; ~RunGuard() { if (q) cudaFree(q); q = nullptr; } } run_guard{d_run};   // freed on every exit path
     BSFM_CUDA_TRY(cudaMemcpyAsync(d_run, run.data(), (size_t) K * sizeof(RunImage), cudaMemcpyHostToDevice, db->stream));
 
     // ---- chunked launches ---------------------------------------------------------------------
@@ -257,7 +269,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     const size_t o_cnt = carve(64);
     const size_t o_cub = carve(cub_bytes);
     int rc = ensure_scratch(db, off);
-    if (rc != BSFM_OK) { cudaFree(d_run); return rc; }
+    if (rc != BSFM_OK) { return rc; }
     uint8_t *S = (uint8_t *) db->scratch;
 
     MatchParams P;
@@ -277,12 +289,13 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     P.match_slot = (uint32_t *) (S + o_slot_a); P.match_idx2 = (int32_t *) (S + o_idx_a); P.match_cap = (int32_t) cap;
     P.counters = (int32_t *) (S + o_cnt);
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the dynamic shared-memory limit is a per-device (per-context) function attribute: set it once per device
+    static std::atomic<int> attr_done[64];
+    if (db->device < 0 || db->device >= 64 || !attr_done[db->device].load(std::memory_order_acquire)) {
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
-        attr_set = true;
+        if (db->device >= 0 && db->device < 64) attr_done[db->device].store(1, std::memory_order_release);
     }
 
     float ms_search = 0.f;
@@ -322,7 +335,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));
             BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
             BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
-            if (h_cnt[2]) { set_error("bsfm_match_run: candidate buffer overflow (internal)"); cudaFree(d_run); return BSFM_ERR_CUDA; }
+            if (h_cnt[2]) { set_error("bsfm_match_run: candidate buffer overflow (internal)"); return BSFM_ERR_CUDA; }
             const int ncand = h_cnt[0];
             if (ncand > 0) {
                 const int64_t threads = (int64_t) ncand * 32;
@@ -330,7 +343,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
                 BSFM_KERNEL_CHECK();
                 BSFM_CUDA_TRY(cudaMemcpyAsync(h_cnt, P.counters, sizeof h_cnt, cudaMemcpyDeviceToHost, db->stream));
                 BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
-                if (h_cnt[2]) { set_error("bsfm_match_run: hard-row buffer overflow (internal)"); cudaFree(d_run); return BSFM_ERR_CUDA; }
+                if (h_cnt[2]) { set_error("bsfm_match_run: hard-row buffer overflow (internal)"); return BSFM_ERR_CUDA; }
                 const int nhard = h_cnt[3];
                 db->hard_rows += nhard; db->cand_rows += ncand;
                 if (nhard > 0) {
@@ -346,11 +359,11 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
             cudaEventElapsedTime(&ms, db->ev[1], db->ev[2]);
             ms_search += ms;
         }
-        if (h_cnt[2]) { set_error("bsfm_match_run: match buffer overflow (internal)"); cudaFree(d_run); return BSFM_ERR_CUDA; }
+        if (h_cnt[2]) { set_error("bsfm_match_run: match buffer overflow (internal)"); return BSFM_ERR_CUDA; }
         const int nmatch = h_cnt[1];
         if (nmatch > 0) {
             rc = grow_matches(db, db->total_matches + nmatch);
-            if (rc != BSFM_OK) { cudaFree(d_run); return rc; }
+            if (rc != BSFM_OK) { return rc; }
             size_t tb = cub_bytes;
             int end_bit = 1;
             while (end_bit < 32 && ((uint64_t) 1 << end_bit) < (uint64_t) (u1 - u0) * TILE_Q) end_bit++;
@@ -368,7 +381,6 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     }
     BSFM_CUDA_TRY(cudaEventRecord(db->ev[3], db->stream));
     BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
-    cudaFree(d_run);
     float ms_total = 0.f;
     cudaEventElapsedTime(&ms_total, db->ev[0], db->ev[3]);
     db->ms[0] = ms_search; db->ms[1] = ms_total - ms_search; db->ms[2] = ms_total;
@@ -483,7 +495,145 @@ int64_t bsfm_match_all_pairs(const uint8_t *keys, const int64_t *key_off, int nu
     return total;
 }
 
-/* MatchKeys(k1 = queries, k2 = database): image 0 = k1, image 1 = k2, the single pair (0,1). */
+}  // extern "C"
+
+/* MatchKeys(k1 = queries, k2 = database): image 0 = k1, image 1 = k2, the single pair (0,1).
+ *
+ * The unmodified KeyMatchFull main calls this once per image pair with the SAME host buffers over and over
+ * (src/KeyMatchFull.cpp:105-151: keys live for the whole run).  Prepared device images (norm-sorted,
+ * swizzled) are therefore cached per (host pointer, key count, 64-bit content hash): a repeated image costs one hash of
+ * its 640 KB instead of an upload, ~10 cudaMallocs and a segmented sort, and the pair runs on a persistent two-image
+ * database filled by device-to-device copies.  BSFM_MATCH_PAIR_CACHE=0 restores the build-per-call path. */
+namespace {
+struct CachedImage { const uint8_t *host; int n; uint64_t hash; bsfm_keydb *db; uint64_t last_use; size_t bytes; };
+struct PairCache {
+    std::mutex mu;
+    std::vector<CachedImage> imgs;
+    uint64_t tick = 0;
+    size_t bytes = 0;
+    int device = -1;
+    bsfm_keydb *pair = nullptr;
+    int64_t pair_rows_cap = 0;
+    void flush()
+    {
+        for (auto &c : imgs) bsfm_keydb_destroy(c.db);
+        imgs.clear(); bytes = 0;
+        if (pair) bsfm_keydb_destroy(pair);
+        pair = nullptr; pair_rows_cap = 0;
+    }
+};
+PairCache g_pair_cache;
+
+uint64_t hash_keys(const uint8_t *p, size_t bytes)      // bytes is a multiple of 128
+{
+    uint64_t h[8] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull,
+                     0x85EBCA77C2B2AE63ull, 0xFF51AFD7ED558CCDull, 0xC4CEB9FE1A85EC53ull, 0x2545F4914F6CDD1Dull};
+    const size_t nw = bytes / 8;
+    for (size_t w = 0; w + 8 <= nw; w += 8) {
+        uint64_t v[8];
+        memcpy(v, p + w * 8, 64);
+        for (int q = 0; q < 8; q++) { h[q] = (h[q] ^ v[q]) * 0x100000001B3ull; h[q] ^= h[q] >> 29; }
+    }
+    uint64_t r = bytes;
+    for (int q = 0; q < 8; q++) r = (r ^ h[q]) * 0x9FB21C651E98DF25ull;
+    return r ^ (r >> 32);
+}
+
+// cached one-image database of (k, n); builds it on a miss.  Caller holds the mutex.
+bsfm_keydb *cached_image(PairCache &C, const uint8_t *k, int n)
+{
+    const uint64_t h = hash_keys(k, (size_t) n * DESC_BYTES);
+    for (auto &c : C.imgs)
+        if (c.n == n && c.hash == h) { c.last_use = ++C.tick; c.host = k; return c.db; }
+    const size_t limit_bytes = (size_t) 8 << 30;
+    while (!C.imgs.empty() && (C.imgs.size() >= 8192 || C.bytes > limit_bytes)) {      // evict the least recently used image
+        size_t victim = 0;
+        for (size_t q = 1; q < C.imgs.size(); q++) if (C.imgs[q].last_use < C.imgs[victim].last_use) victim = q;
+        C.bytes -= C.imgs[victim].bytes;
+        bsfm_keydb_destroy(C.imgs[victim].db);
+        C.imgs.erase(C.imgs.begin() + (long) victim);
+    }
+    int64_t off[2] = {0, n};
+    bsfm_keydb *db = new bsfm_keydb();
+    if (keydb_build(db, k, false, off, 1) != BSFM_OK) { bsfm_keydb_destroy(db); return nullptr; }
+    CachedImage c{k, n, h, db, ++C.tick, (size_t) db->drows * (DESC_BYTES + 8)};
+    C.bytes += c.bytes;
+    C.imgs.push_back(c);
+    return db;
+}
+
+// the persistent two-image database, (re)allocated for at least `rows` device rows
+int ensure_pair_db(PairCache &C, int64_t rows, int device)
+{
+    if (C.pair && C.pair_rows_cap >= rows) return BSFM_OK;
+    if (C.pair) bsfm_keydb_destroy(C.pair);
+    C.pair = nullptr; C.pair_rows_cap = 0;
+    const int64_t cap = rows + rows / 4 + 4 * IMG_PAD;
+    bsfm_keydb *db = new bsfm_keydb();
+    db->N = 2; db->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete db; set_error("cudaGetDeviceProperties failed"); return BSFM_ERR_CUDA; }
+    db->num_sms = prop.multiProcessorCount;
+    C.pair = db;      // bsfm_keydb_destroy releases whatever was allocated if a step below fails
+    BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    for (int e = 0; e < 4; e++) BSFM_CUDA_TRY(cudaEventCreate(&db->ev[e]));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_keys_sw, (size_t) cap * DESC_BYTES));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_norms, (size_t) cap * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_perm, (size_t) cap * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_tile_img, (size_t) (cap / TILE_Q) * sizeof(int32_t)));
+    BSFM_CUDA_TRY(cudaMalloc(&db->d_img_doff, 3 * sizeof(int32_t)));
+    C.pair_rows_cap = cap;
+    return BSFM_OK;
+}
+
+int match_pair_cached(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int32_t *out_pairs, int cap)
+{
+    PairCache &C = g_pair_cache;
+    std::lock_guard<std::mutex> lock(C.mu);
+    int dev = 0;
+    BSFM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != C.device) { C.flush(); C.device = dev; }
+    bsfm_keydb *a = cached_image(C, k1, n1);
+    if (!a) return BSFM_ERR_CUDA;
+    bsfm_keydb *b = cached_image(C, k2, n2);      // may evict, never the entry just touched (it is the most recent)
+    if (!b) return BSFM_ERR_CUDA;
+    const int32_t rows_a = a->doff[1], rows_b = b->doff[1];
+    int rc = ensure_pair_db(C, (int64_t) rows_a + rows_b + IMG_PAD, dev);
+    if (rc != BSFM_OK) return rc;
+    bsfm_keydb *db = C.pair;
+    db->key_off = {0, n1, (int64_t) n1 + n2};
+    db->doff = {0, rows_a, rows_a + rows_b};
+    db->drows = (int64_t) rows_a + rows_b + IMG_PAD;
+    std::vector<int32_t> tile_img((size_t) (db->drows / TILE_Q), -1);
+    for (int32_t t = 0; t < rows_a / TILE_Q; t++) tile_img[(size_t) t] = 0;
+    for (int32_t t = rows_a / TILE_Q; t < (rows_a + rows_b) / TILE_Q; t++) tile_img[(size_t) t] = 1;
+    cudaStream_t st = db->stream;
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_tile_img, tile_img.data(), tile_img.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_img_doff, db->doff.data(), 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // image rows keep their swizzled layout under a copy to any row offset that is a multiple of 8 (here: of 256)
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_keys_sw, a->d_keys_sw, (size_t) rows_a * DESC_BYTES, cudaMemcpyDeviceToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_norms, a->d_norms, (size_t) rows_a * 4, cudaMemcpyDeviceToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_perm, a->d_perm, (size_t) rows_a * 4, cudaMemcpyDeviceToDevice, st));
+    const size_t rb = (size_t) rows_b + IMG_PAD;      // with the spare padded tile that keeps 256-row reads in bounds
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_keys_sw + (size_t) rows_a * DESC_BYTES, b->d_keys_sw, rb * DESC_BYTES, cudaMemcpyDeviceToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_norms + rows_a, b->d_norms, rb * 4, cudaMemcpyDeviceToDevice, st));
+    BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_perm + rows_a, b->d_perm, rb * 4, cudaMemcpyDeviceToDevice, st));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(st));      // tile_img is a host temporary
+    int64_t total = match_run_impl(db, 1, 2, -1, ratio);
+    if (total < 0) return (int) total;
+    if (total > 0) {
+        std::vector<int32_t> m((size_t) total * 2);
+        int32_t pc = 0;
+        rc = bsfm_match_fetch(db, &pc, 1, m.data(), total);
+        if (rc != BSFM_OK) return rc;
+        const int64_t ncopy = std::min<int64_t>(total, cap);
+        if (ncopy > 0 && out_pairs) memcpy(out_pairs, m.data(), (size_t) ncopy * 2 * sizeof(int32_t));
+    }
+    return (int) std::min<int64_t>(total, INT_MAX);
+}
+}  // namespace
+
+extern "C" {
 int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int32_t *out_pairs, int cap)
 {
     clear_error();
@@ -491,6 +641,7 @@ int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double
     int rc = require_device();
     if (rc != BSFM_OK) return rc;
     if (n1 == 0 || n2 == 0) return 0;
+    if (env_int("BSFM_MATCH_PAIR_CACHE", 1) != 0) return match_pair_cached(k1, n1, k2, n2, ratio, out_pairs, cap);
     std::vector<uint8_t> keys((size_t) (n1 + n2) * DESC_BYTES);
     memcpy(keys.data(), k1, (size_t) n1 * DESC_BYTES);
     memcpy(keys.data() + (size_t) n1 * DESC_BYTES, k2, (size_t) n2 * DESC_BYTES);
@@ -509,6 +660,13 @@ int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double
     bsfm_keydb_destroy(db);
     if (total > INT_MAX) total = INT_MAX;
     return (int) total;
+}
+
+/* releases the device images bsfm_match_pair keeps between calls */
+void bsfm_match_pair_cache_clear(void)
+{
+    std::lock_guard<std::mutex> lock(g_pair_cache.mu);
+    g_pair_cache.flush();
 }
 
 }  // extern "C"

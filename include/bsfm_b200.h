@@ -61,6 +61,10 @@ int bsfm_set_device(int device);
  * only the first cap are written and the full count is still returned.                       */
 int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio,
                     int32_t *out_pairs, int cap);
+/* bsfm_match_pair keeps the prepared device image of every key buffer it has seen (keyed by key count and a 64-bit hash
+ * of the contents; the unmodified KeyMatchFull main passes the same buffers for every pair, KeyMatchFull.cpp:105-151),
+ * least recently used images are dropped beyond 8 GB.  This releases them all.                                       */
+void bsfm_match_pair_cache_clear(void);
 
 /* Device-resident key database for the KeyMatchFull all-pairs loop (src/KeyMatchFull.cpp:93-151).
  * keys  : concatenation of all images' descriptors (sum n_i x 128 bytes), HOST memory

@@ -1,7 +1,8 @@
 // key_match_full_b200.cpp -- `KeyMatchFull <list.txt> <outfile> [window_radius]` on the persistent GPU matcher.
 //
-// Same command line, same key files, byte-identical `matches.init.txt` as the reference tool
-// (src/KeyMatchFull.cpp:57-160), but the pair loop (:105-151) is ONE call sequence on the device-resident key
+// Same command line, same key files and a `matches.init.txt` byte-identical to the reference tool RUN IN EXACT MODE
+// (src/KeyMatchFull.cpp:57-160 with max_pts_visit = 0; the stock binary searches its kd-tree approximately with a
+// 200-visit cap, keys2a.h:99-107, so on real data its table can differ from any exact matcher's), but the pair loop (:105-151) is ONE call sequence on the device-resident key
 // database of libbsfm_b200.so (bsfm_keydb_create -> bsfm_match_run -> bsfm_match_fetch) instead of one MatchKeys
 // call per pair, and the key files are parsed by shim/keyfile_b200.cpp on all host cores.
 // The search is exact (== the reference with max_pts_visit = 0).  No CPU matching path: any library error ends

@@ -14,13 +14,20 @@ from bundler_sfm_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
+# include/bsfm_b200_sba.h declares what the link-time replacements of libsba / libsfmdrv export (shim/_build), the other
+# headers what libbsfm_b200.so exports
+SHIM_HEADERS = {"bsfm_b200_sba.h"}
+
+
+def declared_symbols(shim=False):
     names = []
     for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        if (os.path.basename(h) in SHIM_HEADERS) != shim:
+            continue
         src = open(h).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         src = re.sub(r"//[^\n]*", "", src)
-        for m in re.finditer(r"\b((?:bsfm|sba|run)_[a-z0-9_]*)\s*\(", src):
+        for m in re.finditer(r"\b((?:bsfm|sba|sfm|run)_[A-Za-z0-9_]*)\s*\(", src):
             names.append(m.group(1))
     return sorted(set(names))
 
@@ -32,6 +39,22 @@ def test_library_loads_and_exports_all_declared_symbols():
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, missing
     assert b"sm_100a" in lib.bsfm_version()
+
+
+def test_shim_libraries_export_the_reference_driver_symbols():
+    """libsba_b200.so / libsfmdrv_b200.so: the reference's sba drivers, run_sfm and the sfm-driver projection callbacks"""
+    build = os.path.join(ROOT, "shim", "_build")
+    if not os.path.exists(os.path.join(build, "libsba_b200.so")):
+        pytest.skip("shim/_build not built")
+    bundler_sfm_b200.load_library()     # the shims link against libbsfm_b200.so (rpath)
+    drv = ctypes.CDLL(os.path.join(build, "libsfmdrv_b200.so"), mode=ctypes.RTLD_GLOBAL)
+    sba = ctypes.CDLL(os.path.join(build, "libsba_b200.so"))
+    for name in ("sba_motstr_levmar_x", "sba_motstr_levmar", "sba_mot_levmar_x", "sba_mot_levmar"):
+        assert hasattr(sba, name), name
+    for name in ("run_sfm", "sfm_project_point3", "sfm_project_point3_mot"):
+        assert hasattr(drv, name), name
+    for name in declared_symbols(shim=True):
+        assert hasattr(sba, name) or hasattr(drv, name), name
 
 
 def _has_gpu():

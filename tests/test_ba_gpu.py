@@ -5,6 +5,7 @@ GPU box (oracle/_ref when it travelled, else the C restatement) on fresh synthet
 
 Tolerances (BASELINE.json north_star): final reprojection RMSE within 1e-5 px; parameters within 1e-4
 relative, measured per parameter group against the group's largest magnitude."""
+import ctypes
 import os
 
 import numpy as np
@@ -14,6 +15,7 @@ from bundler_sfm_b200 import bundle, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RMSE_TOL = 1e-5
 PARAM_TOL = 1e-4
 
@@ -154,6 +156,31 @@ def test_config3_vs_reference_summary():
     assert rel_group_err(got["R"], np.array(ref["R"])) <= PARAM_TOL
 
 
+def test_config3_equal_iteration_count_vs_reference():
+    """the comparison "at equal iteration count", free of the eps4 = 0 knife-edge that decides where
+    the full config-3 solve stops: both sides run exactly 4 LM iterations with Snavely's stop-8 rule disabled
+    (itmax = 4, opts[5] = 0).  Reference summary: tests/golden/ba_config3_it4_ref.json (unmodified reference, 168 s)."""
+    import json
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ba_config3_it4_ref.json")))
+    scene = synth.ba_scene(1000, 500000, 6, seed=1234)
+    n, m = scene["vmask"].shape
+    nvis = scene["projections"].shape[0]
+    p, cnp = bundle.pack_params(scene)
+    vm = np.ascontiguousarray(scene["vmask"], np.int8)
+    x = np.ascontiguousarray(scene["projections"])
+    its, info = bundle.levmar_model(n, m, vm.ctypes.data, p.ctypes.data, x.ctypes.data, cnp, scene["R"], scene["f"], itmax=4, eps5=0.0)
+    assert its == 4 and int(info[5]) == int(ref["info"][5]) == 4
+    assert int(info[6]) == int(ref["info"][6]) == 3                        # stopped by itmax on both sides
+    assert abs(info[0] - ref["info"][0]) <= 1e-9 * ref["info"][0]           # initial error
+    assert abs(np.sqrt(info[1] / nvis) - np.sqrt(ref["info"][1] / nvis)) <= RMSE_TOL
+    assert int(info[9]) == int(ref["info"][9])                             # same number of linear systems solved
+    got = bundle.unpack_params(p, scene)
+    idx = np.array(ref["pt_idx"])
+    assert rel_group_err(got["pts"][idx], np.array(ref["pts"])) <= PARAM_TOL
+    for key in ("c", "f", "R"):
+        assert rel_group_err(got[key], np.array(ref[key])) <= PARAM_TOL, key
+
+
 def test_mid_size_system_uses_blocked_path_vs_oracle(oracle):
     """200 cameras -> reduced system 1800 x 1800: exercises the large-system Cholesky path (diag/trsm kernels,
     DMMA trailing update, row-oriented back substitution) at a size the CPU reference finishes in seconds"""
@@ -178,6 +205,92 @@ def test_multiwave_system_vs_oracle(oracle):
     got = bundle.run_sfm(scene)
     ref = oracle.run_sfm_oracle(scene)
     check_solution(got, ref, scene["projections"].shape[0], "multiwave500")
+
+
+# ------------------------------------------------------------------------------------------------
+# sba_Axb_Chol (sba_lapack.c:374-485): the dense SPD solve on its own, both Cholesky paths
+# ------------------------------------------------------------------------------------------------
+def _spd(n, seed, spread=2.0):
+    rng = np.random.default_rng(seed)
+    k = max(8, n // 4)
+    G = rng.standard_normal((n, k))
+    S = G @ G.T / k
+    S += np.eye(n) * 1e-3 * np.trace(S) / n
+    d = 10.0 ** rng.uniform(-spread, spread, n)
+    S = S * d[:, None] * d[None, :]
+    return (S + S.T) * 0.5
+
+
+def _axb_chol(A, b):
+    lib = bundle.load_library()
+    fn = lib.bsfm_sba_Axb_Chol
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    fn.restype = ctypes.c_int
+    x = np.zeros(A.shape[0])
+    return fn(A.ctypes.data, b.ctypes.data, x.ctypes.data, A.shape[0], 0), x
+
+
+@pytest.mark.parametrize("n", [9, 450, 1547, 2100, 4000])
+def test_axb_chol_vs_lapack(n):
+    """small path (<= 1536) and the 256-column panel path with the tcgen05 int8-slice trailing update (> 1536), incl. an odd
+    dimension and one that is not a multiple of 32: backward error at the level of LAPACK's, solution close to LAPACK's"""
+    A = _spd(n, seed=n)
+    xt = np.random.default_rng(1).standard_normal(n)
+    b = A @ xt
+    rc, x = _axb_chol(A, b)
+    assert rc == 1
+    xr = np.linalg.solve(A, b)
+    nrm = np.linalg.norm(A, 'fro')
+    res = np.linalg.norm(A @ x - b) / (nrm * np.linalg.norm(x))
+    res_ref = np.linalg.norm(A @ xr - b) / (nrm * np.linalg.norm(xr))
+    assert res <= max(10.0 * res_ref, 1e-14), (n, res, res_ref)
+    # forward error bounded like LAPACK's own (the systems are ill-conditioned by construction: row scales 10^+-2)
+    err, err_ref = np.linalg.norm(x - xt) / np.linalg.norm(xt), np.linalg.norm(xr - xt) / np.linalg.norm(xt)
+    assert err <= max(20.0 * err_ref, 1e-10), (n, err, err_ref)
+
+
+def test_axb_chol_vs_reference_routine(oracle):
+    """the unmodified sba_Axb_Chol (oracle/_ref, dpotrf + dpotrs) on the same system"""
+    lib = oracle.ref_sba()
+    if lib is None:
+        pytest.skip("needs oracle/_ref/libref_sba.so")
+    n = 1800
+    A = _spd(n, seed=3)
+    b = A @ np.random.default_rng(2).standard_normal(n)
+    rc, x = _axb_chol(A, b)
+    fn = lib.sba_Axb_Chol
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    fn.restype = ctypes.c_int
+    xr = np.zeros(n)
+    A2, b2 = A.copy(), b.copy()
+    assert fn(A2.ctypes.data, b2.ctypes.data, xr.ctypes.data, n, 0) == 1 and rc == 1
+    assert np.linalg.norm(x - xr) / np.linalg.norm(xr) <= 1e-7
+
+
+@pytest.mark.parametrize("n", [300, 2000])
+def test_axb_chol_reports_indefinite_matrix(n):
+    """the reference returns 0 when a leading minor is not positive definite (sba_lapack.c:439-442)"""
+    A = _spd(n, seed=5)
+    A[n // 2, n // 2] = -1.0
+    rc, _ = _axb_chol(A, np.ones(n))
+    assert rc == 0
+
+
+def test_axb_chol_tensor_update_equals_dmma_update():
+    """the tcgen05 int8-slice trailing update against the fp64 DMMA update (BSFM_BA_TC=0) in a child process"""
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from tests.test_ba_gpu import _spd, _axb_chol; "
+            "A = _spd(2600, 11); b = A @ np.random.default_rng(4).standard_normal(2600); rc, x = _axb_chol(A, b); "
+            "assert rc == 1; np.save(sys.argv[1], x)") % ROOT
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for tc in ("1", "0"):
+            f = os.path.join(td, f"x{tc}.npy")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, BSFM_BA_TC=tc))
+            outs.append(np.load(f))
+    assert np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[1]) <= 1e-7
 
 
 def test_export_of_U_V_W_S_vs_reference(oracle):

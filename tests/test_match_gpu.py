@@ -143,3 +143,30 @@ def test_tc_equals_dp4a_at_scale(monkeypatch):
     for (j, i), c in zip(p0, c0):
         if i == j + 1:
             assert c > 500
+
+
+def test_config4_table_sampled_pairs_vs_oracle_and_reference_exact(oracle):
+    """BASELINE.json configs[3] at full size (500 images x 5000 keys, 124,750 pairs): 200 randomly drawn image pairs of the
+    GPU table are compared with the CPU oracle (pinned to the reference), and a handful of them with the UNMODIFIED
+    reference MatchKeys in exact mode (max_pts_visit = 0, keys2a.cpp:347-372) when oracle/_ref is present."""
+    N, K = 500, 5000
+    imgs = synth.sift_like_descriptors(N, K, seed=7)
+    pairs, counts, matches = keymatch.key_match_full(imgs, -1, 0.6)
+    assert len(pairs) == N * (N - 1) // 2 and int(counts.sum()) == matches.shape[0] == 1068340
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    rng = np.random.default_rng(2026)
+    picked = rng.choice(len(pairs), 200, replace=False)
+    # make sure rich pairs (consecutive images share 30 % noisy copies) are represented, not only sparse ones
+    rich = [q for q, (j, i) in enumerate(pairs) if i == j + 1][::25]
+    picked = np.unique(np.concatenate([picked, np.array(rich[:20], dtype=picked.dtype)]))
+    have_ref = oracle.ref_match() is not None
+    nref = 0
+    for q in picked:
+        j, i = pairs[q]
+        got = matches[starts[q]:starts[q + 1]]
+        want = oracle.match_pair_port(imgs[j], imgs[i], 0.6)
+        assert np.array_equal(got, want), (j, i)
+        if have_ref and (nref < 3 or (i == j + 1 and nref < 6)):
+            assert np.array_equal(got, oracle.match_pair_ref(imgs[j], imgs[i], 0.6, 0)), ("reference exact mode", j, i)
+            nref += 1
+    assert not have_ref or nref >= 3

@@ -162,3 +162,75 @@ def test_run_sfm_through_reference_signature_shim(oracle):
     nvis = scene["projections"].shape[0]
     assert abs(bundle.reprojection_rmse(scene, got) - np.sqrt(ref["info"][1] / nvis)) <= 1e-5
     assert np.max(np.abs(got["pts"] - ref["pts"])) / np.max(np.abs(ref["pts"])) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# B2: sba_motstr_levmar / sba_mot_levmar with the reference signatures (shim/sba_b200.c), driven by a C program that is
+# compiled against the reference's own sba.h (tests/c/sba_boundary_main.c, built by shim/Makefile)
+# ------------------------------------------------------------------------------------------------
+def _write_scene(path, scene, est_focal=1, undistort=1):
+    vm = np.ascontiguousarray(scene["vmask"], np.int8)
+    n, m = vm.shape
+    proj = np.ascontiguousarray(scene["projections"], np.float64)
+    with open(path, "wb") as f:
+        f.write(np.array([n, m, proj.shape[0], est_focal, undistort], np.int32).tobytes())
+        f.write(vm.tobytes()); f.write(proj.tobytes())
+        cams = np.concatenate([np.asarray(scene["R"], float).reshape(m, 9), np.asarray(scene["c"], float), np.asarray(scene["f"], float)[:, None],
+                               np.asarray(scene["k"], float)], axis=1)
+        f.write(np.ascontiguousarray(cams).tobytes())
+        f.write(np.ascontiguousarray(scene["pts"], np.float64).tobytes())
+
+
+def _read_result(path, scene, cnp):
+    raw = open(path, "rb").read()
+    rc = int(np.frombuffer(raw[:4], np.int32)[0])
+    info = np.frombuffer(raw[4:84], np.float64).copy()
+    p = np.frombuffer(raw[84:], np.float64).copy()
+    return rc, info, p
+
+
+@pytest.mark.gpu
+def test_sba_motstr_levmar_reference_signature_program(tmp_path, oracle):
+    from bundler_sfm_b200 import bundle
+    exe = os.path.join(BUILD, "sba_boundary_test")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_build/sba_boundary_test not built (needs /root/reference headers at build time)")
+    scene = synth.ba_scene(12, 700, 4, seed=77)
+    nvis = scene["projections"].shape[0]
+    _write_scene(tmp_path / "scene.bin", scene)
+    r = subprocess.run([exe, str(tmp_path / "scene.bin"), str(tmp_path / "res.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rc, info, p = _read_result(tmp_path / "res.bin", scene, 9)
+    ref = oracle.run_sfm_oracle(scene)
+    assert rc == int(ref["info"][5]) == int(info[5])                    # returns the iteration count like the reference
+    assert int(info[6]) == int(ref["info"][6])
+    assert abs(np.sqrt(info[1] / nvis) - np.sqrt(ref["info"][1] / nvis)) <= 1e-5
+    assert info[7] == ref["info"][7] and info[8] == ref["info"][8]      # simple driver scales nfev / njev by nvis (sba_levmar_wrap.c:684-695)
+    got = bundle.unpack_params(p, scene)
+    for key in ("R", "c", "f", "pts"):
+        err = np.max(np.linalg.norm((got[key] - ref[key]).reshape(len(ref[key]), -1), axis=1) / np.maximum(np.linalg.norm(np.asarray(ref[key]).reshape(len(ref[key]), -1), axis=1), 1e-12))
+        assert err <= 1e-4, (key, err)
+    # a foreign projection callback is refused loudly with SBA_ERROR (no CPU fallback)
+    r = subprocess.run([exe, "foreign"], capture_output=True, text=True)
+    assert r.returncode == 0 and "foreign rc=-1" in r.stdout and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_sba_mot_levmar_reference_signature_program(tmp_path, oracle):
+    exe = os.path.join(BUILD, "sba_boundary_test")
+    if not os.path.exists(exe) or oracle.ref_sba() is None:
+        pytest.skip("needs shim/_build/sba_boundary_test and oracle/_ref")
+    from bundler_sfm_b200 import bundle
+    scene = synth.ba_scene(10, 500, 4, seed=78)
+    nvis = scene["projections"].shape[0]
+    _write_scene(tmp_path / "scene.bin", scene)
+    r = subprocess.run([exe, str(tmp_path / "scene.bin"), str(tmp_path / "res.bin"), "mot"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rc, info, p = _read_result(tmp_path / "res.bin", scene, 9)
+    ref = oracle.run_sfm_ref(scene, fix_points=1)
+    assert abs(rc - int(ref["info"][5])) <= 3 and int(info[6]) in (2, 4)     # eps4 = 0 knife-edge, see test_ba_gpu.check_mot_solution
+    assert abs(np.sqrt(info[1] / nvis) - np.sqrt(ref["info"][1] / nvis)) <= 1e-5
+    got = bundle.unpack_params(p, scene)
+    assert np.array_equal(got["pts"], np.asarray(scene["pts"], float))          # points untouched
+    for key in ("c", "f"):
+        assert np.max(np.abs(got[key] - ref[key]) / np.maximum(np.abs(ref[key]), 1e-9)) <= 1e-4, key

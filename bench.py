@@ -415,13 +415,14 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
     d_keys = torch.from_numpy(keys).to(dev)
     db = keymatch.KeyDatabase(None, key_off, device_ptr=d_keys.data_ptr())
 
+    # N > 1: the library's own NCCL communicator (one rank per process; the unique id travels through torch.distributed once,
+    # like init_process_group -- outside the timed regions).  The table all-gather runs inside the library over NVLink.
+    comm = keymatch.Comm.from_torch(device=dev) if dist is not None else None
+
     def gather():
-        if dist is None:
+        if comm is None:
             return db.result_dev()[3]
-        # the rank's table stays in HBM: device-to-device copy into torch tensors -> NCCL all-gather over NVLink
-        counts, matches = db.result_to_torch(dev)
-        gc, gm = keymatch.gather_match_table(counts, matches)
-        return gm.shape[0]
+        return db.allgather(comm)
 
     from bundler_sfm_b200 import _lib
     lib = _lib.load_library()
@@ -432,20 +433,19 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
     torch.cuda.synchronize()
     launches0 = lib.bsfm_kernel_launches()
     sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
-    # device time: the library times its launches with CUDA events on ITS stream (bsfm_match_last_timing); the
-    # NCCL gather runs on torch's stream and is timed with torch events; wall clock is kept as a cross-check
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # device time: the library times its launches with CUDA events on ITS stream (bsfm_match_last_timing); the NCCL table
+    # all-gather (also on the library's stream, synchronised before it returns) is timed around the call; wall clock of the
+    # whole pass is kept as a cross-check
     search_ms, dev_ms, total_matches = 0.0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(steps):
         db.run(b, e, -1, 0.6)
         tm = db.timing()
-        ev0.record()
-        total_matches = gather()
-        ev1.record()
-        torch.cuda.synchronize()
+        tg = time.perf_counter()
+        total_matches = gather()          # host-synchronous (the library synchronises its stream): wall clock = device time + launch latency
+        gather_ms = 1e3 * (time.perf_counter() - tg)
         search_ms += tm["search_ms"]
-        dev_ms += tm["total_ms"] + ev0.elapsed_time(ev1)
+        dev_ms += tm["total_ms"] + gather_ms
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = lib.bsfm_kernel_launches() - launches0
@@ -453,14 +453,20 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
         dist.barrier()
     # e2e: host descriptors (pinned) -> upload -> run -> gather -> table on the host
     keys_pin, _keep_keys = pinned_view(torch, keys)
-    t0 = time.perf_counter()
-    db2 = keymatch.KeyDatabase(keys_pin, key_off)
-    db2.run(b, e, -1, 0.6)
-    c_host, m_host = db2.fetch()
     if dist is not None:
-        keymatch.gather_match_table(c_host, m_host, device=dev)
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    db2 = keymatch.KeyDatabase(keys_pin, key_off, comm=comm)      # N > 1: every rank uploads and prepares 1/N of the images
+    db2.run(b, e, -1, 0.6)
+    if comm is not None:
+        db2.allgather(comm)
+        c_host, m_host = db2.gathered_fetch()                    # the whole table on the host of every rank
+    else:
+        c_host, m_host = db2.fetch()
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - t0
+    e2e_matches = int(m_host.shape[0])
     db2.close()
     t = torch.tensor([dev_ms * 1e-3, search_ms * 1e-3, e2e_wall, wall], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -469,6 +475,9 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
     npairs = num_images * (num_images - 1) // 2
     dp = float(npairs) * keys_per_image * keys_per_image
     db.close()
+    if comm is not None:
+        comm.close()
+    assert e2e_matches == int(total_matches), (e2e_matches, total_matches)
     return {"desc_pairs_per_s": dp * steps / dev_s, "image_pairs_per_s": npairs * steps / dev_s, "ms_per_pass": 1e3 * dev_s / steps,
             "wall_ms_per_pass": 1e3 * wall / steps, "launches": int(launches), "clocks": clocks,
             "search_kernel_ms_per_pass_max_rank": 1e3 * search_s / steps, "int8_tops_search_kernel": dp * 256 / world / (search_s / steps) / 1e12,

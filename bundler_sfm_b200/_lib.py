@@ -58,6 +58,24 @@ def load_library():
     lib.bsfm_match_all_pairs.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_double,
                                          c.c_void_p, c.c_int64, c.c_void_p, c.c_int64]
     lib.bsfm_match_all_pairs.restype = c.c_int64
+    lib.bsfm_comm_unique_id.argtypes = [c.c_void_p]
+    lib.bsfm_comm_unique_id.restype = c.c_int
+    lib.bsfm_comm_create.argtypes = [c.c_void_p, c.c_int, c.c_int]
+    lib.bsfm_comm_create.restype = c.c_void_p
+    lib.bsfm_comm_destroy.argtypes = [c.c_void_p]
+    lib.bsfm_comm_destroy.restype = None
+    lib.bsfm_keydb_create_sharded.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int]
+    lib.bsfm_keydb_create_sharded.restype = c.c_void_p
+    lib.bsfm_match_shard_range.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int)]
+    lib.bsfm_match_shard_range.restype = c.c_int
+    lib.bsfm_match_allgather.argtypes = [c.c_void_p, c.c_void_p]
+    lib.bsfm_match_allgather.restype = c.c_int64
+    lib.bsfm_match_gathered_fetch.argtypes = [c.c_void_p, i64p, i64p, c.c_void_p, c.c_int64, c.c_void_p, c.c_int64]
+    lib.bsfm_match_gathered_fetch.restype = c.c_int
+    lib.bsfm_match_all_pairs_multi.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_double, c.c_int, c.c_void_p,
+                                               c.c_void_p, c.c_int64, c.c_void_p, c.c_int64]
+    lib.bsfm_match_all_pairs_multi.restype = c.c_int64
+    lib.bsfm_match_pair_cache_clear.restype = None
     _LIB = lib
     return lib
 

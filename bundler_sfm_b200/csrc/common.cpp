@@ -66,5 +66,11 @@ int bsfm_set_device(int device)
     }
     return BSFM_OK;
 }
+int bsfm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
 
 }  // extern "C"

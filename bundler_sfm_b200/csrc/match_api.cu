@@ -11,13 +11,14 @@
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace bsfm {
 namespace match {
 // kernels (match_kernels.cu)
 __global__ void raw_norm_kernel(const uint8_t *, int64_t, int32_t *, int32_t *);
-__global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, const int32_t *, const int32_t *, const int32_t *, uint8_t *, int32_t *, int32_t *, int64_t);
+__global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, const int32_t *, const int32_t *, const int32_t *, uint8_t *, int32_t *, int32_t *, int64_t, int64_t, int64_t);
 __global__ void match_dp4a_kernel(MatchParams);
 __global__ void match_tc_kernel(MatchParams);
 __global__ void match_tc_bound_kernel(MatchParams);
@@ -37,7 +38,8 @@ struct bsfm_keydb {
     int device = 0;
     int num_sms = 0;
     std::vector<int64_t> key_off;   // N+1
-    std::vector<int32_t> doff;      // N+1 device row offsets (multiples of 256)
+    std::vector<int32_t> doff;      // N+1 device row offsets (multiples of 256); a sharded build leaves gaps between groups
+    std::vector<int32_t> img_rows;  // N padded row counts
     int64_t drows = 0;
     uint8_t *d_keys_sw = nullptr;
     int32_t *d_norms = nullptr;
@@ -59,6 +61,63 @@ struct bsfm_keydb {
     // scratch reused across runs
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    // table gathered from all ranks (bsfm_match_allgather)
+    int32_t *d_gather_counts = nullptr, *d_gather_matches = nullptr;
+    int64_t gather_pairs = 0, gather_matches = 0, gather_pair_cap = 0, gather_match_cap = 0;
+};
+
+// ---- NCCL, bound at run time (dlopen): libbsfm_b200.so has no link-time dependency on it, single-GPU users never load
+// it, and inside a torch process the already loaded libnccl.so.2 is the one that answers ------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api()
+{
+    static NcclApi api = []() {
+        NcclApi a;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId)) dlsym(a.handle, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank)) dlsym(a.handle, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy)) dlsym(a.handle, "ncclCommDestroy");
+        a.AllGather = (decltype(a.AllGather)) dlsym(a.handle, "ncclAllGather");
+        a.Broadcast = (decltype(a.Broadcast)) dlsym(a.handle, "ncclBroadcast");
+        a.GroupStart = (decltype(a.GroupStart)) dlsym(a.handle, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd)) dlsym(a.handle, "ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString)) dlsym(a.handle, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.Broadcast && a.GroupStart && a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+#define BSFM_NCCL_TRY(expr)                                                                                      \
+    do {                                                                                                          \
+        ncclResult_t r__ = (expr);                                                                                \
+        if (r__ != ncclSuccess) {                                                                                 \
+            set_error("%s failed: %s (%s:%d)", #expr, nccl_api().GetErrorString(r__), __FILE__, __LINE__);        \
+            return BSFM_ERR_CUDA;                                                                                 \
+        }                                                                                                         \
+    } while (0)
+
+struct bsfm_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
 };
 
 static int env_int(const char *name, int dflt)
@@ -67,7 +126,10 @@ static int env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
-static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device, const int64_t *key_off, int N)
+// `comm` != null: cooperative build -- the images are split into `world` contiguous groups of (nearly) equal key count,
+// this rank uploads / sorts / swizzles only ITS group into its chunk of the device layout (chunks of equal size, so the
+// prepared rows are exchanged by ONE in-place ncclAllGather per array over NVLink) and ends with the complete database.
+static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device, const int64_t *key_off, int N, const bsfm_comm *comm = nullptr)
 {
     int rc = require_device();
     if (rc != BSFM_OK) return rc;
@@ -82,20 +144,38 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
     db->num_sms = prop.multiProcessorCount;
     db->key_off.assign(key_off, key_off + N + 1);
     db->doff.resize(N + 1);
-    int64_t r = 0;
-    for (int i = 0; i < N; i++) {
-        int64_t n = key_off[i + 1] - key_off[i];
-        if (n < 0) { set_error("bsfm_keydb_create: key_off not monotone at %d", i); return BSFM_ERR_ARG; }
-        db->doff[i] = (int32_t) r;
-        r += (n + IMG_PAD - 1) / IMG_PAD * IMG_PAD;
-        if (r > (int64_t) INT_MAX - 1024) { set_error("bsfm_keydb_create: more than 2^31 descriptor rows"); return BSFM_ERR_ARG; }
+    for (int i = 0; i < N; i++)
+        if (key_off[i + 1] < key_off[i]) { set_error("bsfm_keydb_create: key_off not monotone at %d", i); return BSFM_ERR_ARG; }
+    const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+    // image groups [gb[g], gb[g+1]) of (nearly) equal key count; one group = everything when not sharded
+    std::vector<int> gb((size_t) world + 1, N);
+    gb[0] = 0;
+    {
+        const int64_t total = key_off[N];
+        int g = 1;
+        for (int i = 0; i < N && g < world; i++)
+            while (g < world && key_off[i + 1] * world >= total * g) gb[(size_t) g++] = i + 1;
     }
-    db->doff[N] = (int32_t) r;
-    db->drows = r + IMG_PAD;   // one spare padded tile so any 256-row read stays in bounds
+    auto padded = [&](int i) { return (key_off[i + 1] - key_off[i] + IMG_PAD - 1) / IMG_PAD * IMG_PAD; };
+    int64_t chunk_rows = 0;
+    for (int g = 0; g < world; g++) {
+        int64_t rows = 0;
+        for (int i = gb[(size_t) g]; i < gb[(size_t) g + 1]; i++) rows += padded(i);
+        chunk_rows = std::max(chunk_rows, rows);
+    }
+    if (chunk_rows * world > (int64_t) INT_MAX - 1024) { set_error("bsfm_keydb_create: more than 2^31 descriptor rows"); return BSFM_ERR_ARG; }
+    for (int g = 0; g < world; g++) {
+        int64_t r = (int64_t) g * chunk_rows;
+        for (int i = gb[(size_t) g]; i < gb[(size_t) g + 1]; i++) { db->doff[i] = (int32_t) r; r += padded(i); }
+    }
+    db->doff[N] = (int32_t) (chunk_rows * world);
+    db->drows = chunk_rows * world + IMG_PAD;   // one spare padded tile so any 256-row read stays in bounds
     const int64_t ntiles = db->drows / TILE_Q;
     std::vector<int32_t> tile_img((size_t) ntiles, -1);
     for (int i = 0; i < N; i++)
-        for (int64_t t = db->doff[i] / TILE_Q; t < db->doff[i + 1] / TILE_Q; t++) tile_img[(size_t) t] = i;
+        for (int64_t t = db->doff[i] / TILE_Q; t < (db->doff[i] + padded(i)) / TILE_Q; t++) tile_img[(size_t) t] = i;
+    db->img_rows.resize(N);
+    for (int i = 0; i < N; i++) db->img_rows[(size_t) i] = (int32_t) padded(i);
 
     BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
     for (int e = 0; e < 4; e++) BSFM_CUDA_TRY(cudaEventCreate(&db->ev[e]));
@@ -107,7 +187,11 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
     BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_tile_img, tile_img.data(), (size_t) ntiles * sizeof(int32_t), cudaMemcpyHostToDevice, db->stream));
     BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_img_doff, db->doff.data(), (size_t) (N + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, db->stream));
 
-    const int64_t total_keys = key_off[N];
+    // this rank's group of images: keys [kb, ke), images [ib, ie), device rows [row_b, row_e)
+    const int ib = gb[(size_t) rank], ie = gb[(size_t) rank + 1];
+    const int64_t kb = key_off[ib], ke = key_off[ie];
+    const int64_t total_keys = ke - kb;
+    const int64_t row_b = (int64_t) rank * chunk_rows, row_e = row_b + chunk_rows;
     uint8_t *d_raw = nullptr;
     int64_t *d_key_off = nullptr;
     // temporaries are released on every exit path (an early BSFM_CUDA_TRY return used to leak them)
@@ -120,43 +204,58 @@ static int keydb_build(bsfm_keydb *db, const uint8_t *keys, bool keys_on_device,
     temps.own(d_key_off);
     BSFM_CUDA_TRY(cudaMemcpyAsync(d_key_off, key_off, (size_t) (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, db->stream));
     if (keys_on_device) {
-        d_raw = const_cast<uint8_t *>(keys);
+        d_raw = const_cast<uint8_t *>(keys) + (size_t) kb * DESC_BYTES;
     } else if (total_keys > 0) {
         BSFM_CUDA_TRY(cudaMalloc(&d_raw, (size_t) total_keys * DESC_BYTES));
         temps.own(d_raw);
-        BSFM_CUDA_TRY(cudaMemcpyAsync(d_raw, keys, (size_t) total_keys * DESC_BYTES, cudaMemcpyHostToDevice, db->stream));
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_raw, keys + (size_t) kb * DESC_BYTES, (size_t) total_keys * DESC_BYTES, cudaMemcpyHostToDevice, db->stream));
     }
     // per-image stable sort of the keys by squared norm (the tensor-core epilogue relies on norm-sorted chunks)
     int32_t *d_nraw = nullptr, *d_nsorted = nullptr, *d_iota = nullptr, *d_src = nullptr, *d_seg = nullptr;
     void *d_tmp = nullptr;
-    if (total_keys > (int64_t) INT_MAX - 1) { set_error("bsfm_keydb_create: more than 2^31 keys"); return BSFM_ERR_ARG; }
+    if (key_off[N] > (int64_t) INT_MAX - 1) { set_error("bsfm_keydb_create: more than 2^31 keys"); return BSFM_ERR_ARG; }
     const size_t nk = (size_t) std::max<int64_t>(total_keys, 1);
+    const int nseg = ie - ib;
     BSFM_CUDA_TRY(cudaMalloc(&d_nraw, nk * 4)); temps.own(d_nraw);
     BSFM_CUDA_TRY(cudaMalloc(&d_nsorted, nk * 4)); temps.own(d_nsorted);
     BSFM_CUDA_TRY(cudaMalloc(&d_iota, nk * 4)); temps.own(d_iota);
     BSFM_CUDA_TRY(cudaMalloc(&d_src, nk * 4)); temps.own(d_src);
-    BSFM_CUDA_TRY(cudaMalloc(&d_seg, (size_t) (N + 1) * 4)); temps.own(d_seg);
+    BSFM_CUDA_TRY(cudaMalloc(&d_seg, (size_t) (nseg + 1) * 4)); temps.own(d_seg);
     if (total_keys > 0) {
-        std::vector<int32_t> seg((size_t) N + 1);
-        for (int i = 0; i <= N; i++) seg[(size_t) i] = (int32_t) key_off[i];
-        BSFM_CUDA_TRY(cudaMemcpyAsync(d_seg, seg.data(), (size_t) (N + 1) * 4, cudaMemcpyHostToDevice, db->stream));
+        std::vector<int32_t> seg((size_t) nseg + 1);
+        for (int i = 0; i <= nseg; i++) seg[(size_t) i] = (int32_t) (key_off[ib + i] - kb);
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_seg, seg.data(), (size_t) (nseg + 1) * 4, cudaMemcpyHostToDevice, db->stream));
         raw_norm_kernel<<<(unsigned) ((total_keys + 7) / 8), 256, 0, db->stream>>>(d_raw, total_keys, d_nraw, d_iota);
         BSFM_KERNEL_CHECK();
         size_t tb = 0;
-        cub::DeviceSegmentedSort::StableSortPairs(nullptr, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, N, d_seg, d_seg + 1, db->stream);
+        cub::DeviceSegmentedSort::StableSortPairs(nullptr, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, nseg, d_seg, d_seg + 1, db->stream);
         BSFM_CUDA_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tb, 1)));
         temps.own(d_tmp);
-        cub::DeviceSegmentedSort::StableSortPairs(d_tmp, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, N, d_seg, d_seg + 1, db->stream);
+        cub::DeviceSegmentedSort::StableSortPairs(d_tmp, tb, d_nraw, d_nsorted, d_iota, d_src, (int) total_keys, nseg, d_seg, d_seg + 1, db->stream);
         count_launch(3);
         BSFM_CUDA_TRY(cudaGetLastError());
         BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));   // seg[] is a host temporary
     }
     {
         const int warps_per_block = 8;
-        const int64_t blocks = (db->drows + warps_per_block - 1) / warps_per_block;
-        prep_kernel<<<(unsigned) blocks, warps_per_block * 32, 0, db->stream>>>(d_raw, d_key_off, db->d_img_doff, db->d_tile_img, d_src, d_nsorted,
-                                                                                 db->d_keys_sw, db->d_norms, db->d_perm, db->drows);
-        BSFM_KERNEL_CHECK();
+        // own chunk, then the spare tile behind the last chunk (padding rows; every rank writes its own copy)
+        const int64_t spans[2][2] = {{row_b, row_e}, {chunk_rows * world, db->drows}};
+        for (int q = 0; q < 2; q++) {
+            const int64_t rows = spans[q][1] - spans[q][0];
+            if (rows <= 0) continue;
+            const int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
+            prep_kernel<<<(unsigned) blocks, warps_per_block * 32, 0, db->stream>>>(d_raw, d_key_off, db->d_img_doff, db->d_tile_img, d_src, d_nsorted,
+                                                                                     db->d_keys_sw, db->d_norms, db->d_perm, spans[q][0], spans[q][1], kb);
+            BSFM_KERNEL_CHECK();
+        }
+    }
+    if (comm && world > 1) {
+        NcclApi &nc = nccl_api();
+        BSFM_NCCL_TRY(nc.GroupStart());
+        BSFM_NCCL_TRY(nc.AllGather(db->d_keys_sw + (size_t) row_b * DESC_BYTES, db->d_keys_sw, (size_t) chunk_rows * DESC_BYTES, ncclUint8, comm->comm, db->stream));
+        BSFM_NCCL_TRY(nc.AllGather(db->d_norms + row_b, db->d_norms, (size_t) chunk_rows, ncclInt32, comm->comm, db->stream));
+        BSFM_NCCL_TRY(nc.AllGather(db->d_perm + row_b, db->d_perm, (size_t) chunk_rows, ncclInt32, comm->comm, db->stream));
+        BSFM_NCCL_TRY(nc.GroupEnd());
     }
     BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
     return BSFM_OK;
@@ -212,7 +311,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
         if (n_i > 0 && units > 0) {
             RunImage R;
             R.img = i; R.n = (int32_t) n_i; R.db_row0 = db->doff[i];
-            R.ntiles_db = (db->doff[i + 1] - db->doff[i]) / TILE_DB;
+            R.ntiles_db = db->img_rows[(size_t) i] / TILE_DB;
             R.atile0 = db->doff[s] / TILE_Q; R.start_img = s;
             R.unit0 = (int32_t) nunits; R.nunits = units; R.pair0 = npairs;
             if (nunits + units > (int64_t) INT_MAX / 2) { set_error("bsfm_match_run: shard too large (work units overflow)"); return BSFM_ERR_ARG; }
@@ -281,7 +380,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     P.hard = (int32_t *) (S + o_hard);
     // 1 = bound epilogue (default; needs every image to fit the kernel's norm staging buffer), 0 = exact chunk minima
     int32_t max_img_rows = 0;
-    for (int i = 0; i < db->N; i++) max_img_rows = std::max(max_img_rows, db->doff[i + 1] - db->doff[i]);
+    for (int i = 0; i < db->N; i++) max_img_rows = std::max(max_img_rows, db->img_rows[(size_t) i]);
     P.epi_mode = (env_int("BSFM_MATCH_EPILOGUE", 1) == 1 && max_img_rows <= TC_NORM_CAP) ? 1 : 0;
     // cta_group::2 kernel (CTA pairs, half the L2 -> SM traffic) vs one CTA per unit (default: measured faster, the
     // path is bound by the TMEM -> register read of the epilogue, not by L2)
@@ -413,7 +512,7 @@ void bsfm_keydb_destroy(bsfm_keydb *db)
 {
     if (!db) return;
     cudaFree(db->d_keys_sw); cudaFree(db->d_norms); cudaFree(db->d_perm); cudaFree(db->d_tile_img); cudaFree(db->d_img_doff);
-    cudaFree(db->d_pair_counts); cudaFree(db->d_matches); cudaFree(db->scratch);
+    cudaFree(db->d_pair_counts); cudaFree(db->d_matches); cudaFree(db->scratch); cudaFree(db->d_gather_counts); cudaFree(db->d_gather_matches);
     for (int e = 0; e < 4; e++) if (db->ev[e]) cudaEventDestroy(db->ev[e]);
     if (db->stream) cudaStreamDestroy(db->stream);
     delete db;
@@ -597,12 +696,13 @@ int match_pair_cached(const uint8_t *k1, int n1, const uint8_t *k2, int n2, doub
     if (!a) return BSFM_ERR_CUDA;
     bsfm_keydb *b = cached_image(C, k2, n2);      // may evict, never the entry just touched (it is the most recent)
     if (!b) return BSFM_ERR_CUDA;
-    const int32_t rows_a = a->doff[1], rows_b = b->doff[1];
+    const int32_t rows_a = a->img_rows[0], rows_b = b->img_rows[0];
     int rc = ensure_pair_db(C, (int64_t) rows_a + rows_b + IMG_PAD, dev);
     if (rc != BSFM_OK) return rc;
     bsfm_keydb *db = C.pair;
     db->key_off = {0, n1, (int64_t) n1 + n2};
     db->doff = {0, rows_a, rows_a + rows_b};
+    db->img_rows = {rows_a, rows_b};
     db->drows = (int64_t) rows_a + rows_b + IMG_PAD;
     std::vector<int32_t> tile_img((size_t) (db->drows / TILE_Q), -1);
     for (int32_t t = 0; t < rows_a / TILE_Q; t++) tile_img[(size_t) t] = 0;
@@ -660,6 +760,210 @@ int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double
     bsfm_keydb_destroy(db);
     if (total > INT_MAX) total = INT_MAX;
     return (int) total;
+}
+
+/* ---- multi-GPU behind the C ABI (KeyMatchFull.cpp:105-151 sharded by database image) --------------------- */
+int bsfm_comm_unique_id(unsigned char id[BSFM_COMM_ID_BYTES])
+{
+    clear_error();
+    NcclApi &nc = nccl_api();
+    if (!nc.ok) { set_error("NCCL (libnccl.so.2) could not be loaded: the multi-GPU entry points need it"); return BSFM_ERR_UNSUPPORTED; }
+    static_assert(sizeof(ncclUniqueId) <= BSFM_COMM_ID_BYTES, "id buffer");
+    ncclUniqueId u;
+    BSFM_NCCL_TRY(nc.GetUniqueId(&u));
+    memset(id, 0, BSFM_COMM_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return BSFM_OK;
+}
+
+bsfm_comm *bsfm_comm_create(const unsigned char id[BSFM_COMM_ID_BYTES], int rank, int world_size)
+{
+    clear_error();
+    if (require_device() != BSFM_OK) return nullptr;
+    NcclApi &nc = nccl_api();
+    if (!nc.ok) { set_error("NCCL (libnccl.so.2) could not be loaded: the multi-GPU entry points need it"); return nullptr; }
+    if (!id || world_size < 1 || rank < 0 || rank >= world_size) { set_error("bsfm_comm_create: bad arguments"); return nullptr; }
+    bsfm_comm *c = new bsfm_comm();
+    c->rank = rank; c->world = world_size;
+    if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; set_error("cudaGetDevice failed"); return nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    ncclResult_t r = nc.CommInitRank(&c->comm, world_size, u, rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", nc.GetErrorString(r)); delete c; return nullptr; }
+    return c;
+}
+
+void bsfm_comm_destroy(bsfm_comm *c)
+{
+    if (!c) return;
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    delete c;
+}
+
+bsfm_keydb *bsfm_keydb_create_sharded(bsfm_comm *comm, const uint8_t *keys, const int64_t *key_off, int num_images)
+{
+    clear_error();
+    if (!comm) { set_error("bsfm_keydb_create_sharded: null communicator"); return nullptr; }
+    bsfm_keydb *db = new bsfm_keydb();
+    if (keydb_build(db, keys, false, key_off, num_images, comm) != BSFM_OK) { bsfm_keydb_destroy(db); return nullptr; }
+    return db;
+}
+
+int bsfm_match_shard_range(const int64_t *key_off, int num_images, int window_radius, int world_size, int rank, int *img_begin, int *img_end)
+{
+    clear_error();
+    if (!key_off || num_images < 0 || world_size < 1 || rank < 0 || rank >= world_size || !img_begin || !img_end) { set_error("bsfm_match_shard_range: bad arguments"); return BSFM_ERR_ARG; }
+    // contiguous database-image ranges of (nearly) equal work n_i * sum_{j in window} n_j (the rule of keymatch.shard_images)
+    std::vector<double> work((size_t) num_images);
+    double total = 0.0;
+    for (int i = 0; i < num_images; i++) {
+        const int s0 = start_image(i, window_radius);
+        work[(size_t) i] = (double) (key_off[i + 1] - key_off[i]) * (double) (key_off[i] - key_off[s0]);
+        total += work[(size_t) i];
+    }
+    std::vector<int> bounds;
+    bounds.push_back(0);
+    double acc = 0.0;
+    int r = 1;
+    for (int i = 0; i < num_images; i++) {
+        acc += work[(size_t) i];
+        while (r < world_size && acc >= total * r / world_size) { bounds.push_back(i + 1); r++; }
+    }
+    while ((int) bounds.size() < world_size) bounds.push_back(num_images);
+    bounds.push_back(num_images);
+    for (size_t q = 1; q < bounds.size(); q++) bounds[q] = std::max(std::min(bounds[q], num_images), bounds[q - 1]);
+    *img_begin = bounds[(size_t) rank]; *img_end = bounds[(size_t) rank + 1];
+    return BSFM_OK;
+}
+
+int64_t bsfm_match_allgather(bsfm_comm *comm, bsfm_keydb *db)
+{
+    clear_error();
+    if (!comm || !db) { set_error("bsfm_match_allgather: null argument"); return BSFM_ERR_ARG; }
+    NcclApi &nc = nccl_api();
+    const int W = comm->world;
+    BSFM_CUDA_TRY(cudaSetDevice(db->device));
+    // 1. sizes of every rank's table
+    int64_t *d_sizes = nullptr;
+    BSFM_CUDA_TRY(cudaMalloc(&d_sizes, (size_t) W * 2 * sizeof(int64_t)));
+    struct Guard { void *q; ~Guard() { cudaFree(q); } } guard{d_sizes};
+    const int64_t mine[2] = {db->shard_pairs, db->total_matches};
+    BSFM_CUDA_TRY(cudaMemcpyAsync(d_sizes + 2 * comm->rank, mine, sizeof mine, cudaMemcpyHostToDevice, db->stream));
+    BSFM_NCCL_TRY(nc.AllGather(d_sizes + 2 * comm->rank, d_sizes, 2, ncclInt64, comm->comm, db->stream));
+    std::vector<int64_t> sizes((size_t) W * 2);
+    BSFM_CUDA_TRY(cudaMemcpyAsync(sizes.data(), d_sizes, sizes.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, db->stream));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    int64_t tp = 0, tm = 0;
+    for (int r = 0; r < W; r++) { tp += sizes[(size_t) 2 * r]; tm += sizes[(size_t) 2 * r + 1]; }
+    if (tp > db->gather_pair_cap) {
+        cudaFree(db->d_gather_counts); db->d_gather_counts = nullptr; db->gather_pair_cap = 0;
+        BSFM_CUDA_TRY(cudaMalloc(&db->d_gather_counts, (size_t) std::max<int64_t>(tp, 1) * sizeof(int32_t)));
+        db->gather_pair_cap = std::max<int64_t>(tp, 1);
+    }
+    if (tm > db->gather_match_cap) {
+        cudaFree(db->d_gather_matches); db->d_gather_matches = nullptr; db->gather_match_cap = 0;
+        BSFM_CUDA_TRY(cudaMalloc(&db->d_gather_matches, (size_t) std::max<int64_t>(tm, 1) * 2 * sizeof(int32_t)));
+        db->gather_match_cap = std::max<int64_t>(tm, 1);
+    }
+    // 2. payload: rank r's counts and matches go to their offsets in the concatenated table (one grouped broadcast per rank:
+    //    shards are contiguous database-image ranges in rank order, so the concatenation IS the KeyMatchFull order)
+    BSFM_NCCL_TRY(nc.GroupStart());
+    int64_t op = 0, om = 0;
+    for (int r = 0; r < W; r++) {
+        const int64_t np = sizes[(size_t) 2 * r], nm = sizes[(size_t) 2 * r + 1];
+        if (np > 0) BSFM_NCCL_TRY(nc.Broadcast(db->d_pair_counts, db->d_gather_counts + op, (size_t) np, ncclInt32, r, comm->comm, db->stream));
+        if (nm > 0) BSFM_NCCL_TRY(nc.Broadcast(db->d_matches, db->d_gather_matches + 2 * om, (size_t) nm * 2, ncclInt32, r, comm->comm, db->stream));
+        op += np; om += nm;
+    }
+    BSFM_NCCL_TRY(nc.GroupEnd());
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    db->gather_pairs = tp; db->gather_matches = tm;
+    return tm;
+}
+
+int bsfm_match_gathered_fetch(bsfm_keydb *db, int64_t *num_pairs, int64_t *num_matches, int32_t *pair_counts, int64_t pair_cap, int32_t *matches, int64_t match_cap)
+{
+    clear_error();
+    if (!db) { set_error("bsfm_match_gathered_fetch: null db"); return BSFM_ERR_ARG; }
+    if (num_pairs) *num_pairs = db->gather_pairs;
+    if (num_matches) *num_matches = db->gather_matches;
+    if (!pair_counts && !matches) return BSFM_OK;
+    if (pair_cap < db->gather_pairs || match_cap < db->gather_matches) {
+        set_error("bsfm_match_gathered_fetch: need %lld pairs / %lld matches, got %lld / %lld", (long long) db->gather_pairs,
+                  (long long) db->gather_matches, (long long) pair_cap, (long long) match_cap);
+        return BSFM_ERR_CAPACITY;
+    }
+    if (db->gather_pairs > 0 && pair_counts)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(pair_counts, db->d_gather_counts, (size_t) db->gather_pairs * sizeof(int32_t), cudaMemcpyDefault, db->stream));
+    if (db->gather_matches > 0 && matches)
+        BSFM_CUDA_TRY(cudaMemcpyAsync(matches, db->d_gather_matches, (size_t) db->gather_matches * 2 * sizeof(int32_t), cudaMemcpyDefault, db->stream));
+    BSFM_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    return BSFM_OK;
+}
+
+}  // extern "C"
+
+#include <thread>
+namespace {
+struct MultiShared {
+    const uint8_t *keys; const int64_t *key_off; int N, window; double ratio; int ngpus; const int *devices;
+    unsigned char id[BSFM_COMM_ID_BYTES];
+    int32_t *pair_counts; int64_t pair_cap; int32_t *matches; int64_t match_cap;
+    std::vector<int64_t> result; std::vector<std::string> errors; std::vector<float> search_ms;
+};
+void multi_worker(MultiShared *S, int rank)
+{
+    auto fail = [&](int64_t code) { S->result[(size_t) rank] = code; S->errors[(size_t) rank] = last_error(); };
+    if (cudaSetDevice(S->devices ? S->devices[rank] : rank) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", S->devices ? S->devices[rank] : rank); return fail(BSFM_ERR_CUDA); }
+    bsfm_comm *comm = bsfm_comm_create(S->id, rank, S->ngpus);
+    if (!comm) return fail(BSFM_ERR_CUDA);
+    bsfm_keydb *db = bsfm_keydb_create_sharded(comm, S->keys, S->key_off, S->N);
+    int64_t total = BSFM_ERR_CUDA;
+    if (db) {
+        int b = 0, e = 0;
+        bsfm_match_shard_range(S->key_off, S->N, S->window, S->ngpus, rank, &b, &e);
+        total = bsfm_match_run(db, b, e, S->window, S->ratio);
+        S->search_ms[(size_t) rank] = db->ms[0];
+        // every rank must enter the collective, also after a local failure: contribute an empty table then
+        if (total < 0) { S->errors[(size_t) rank] = last_error(); db->shard_pairs = 0; db->total_matches = 0; }
+        const int64_t g = bsfm_match_allgather(comm, db);
+        if (total >= 0) total = g;
+        if (total >= 0 && rank == 0) {
+            int rc = bsfm_match_gathered_fetch(db, nullptr, nullptr, S->pair_counts, S->pair_cap, S->matches, S->match_cap);
+            if (rc != BSFM_OK) total = rc;
+        }
+    }
+    if (total < 0 && S->errors[(size_t) rank].empty()) S->errors[(size_t) rank] = last_error();
+    S->result[(size_t) rank] = total;
+    if (db) bsfm_keydb_destroy(db);
+    bsfm_comm_destroy(comm);
+}
+}  // namespace
+
+extern "C" {
+int64_t bsfm_match_all_pairs_multi(const uint8_t *keys, const int64_t *key_off, int num_images, int window_radius, double ratio,
+                                   int ngpus, const int *devices, int32_t *pair_counts, int64_t pair_cap, int32_t *matches, int64_t match_cap)
+{
+    clear_error();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available: libbsfm_b200 has no CPU fallback"); return BSFM_ERR_NO_DEVICE; }
+    if (ngpus < 1 || ngpus > ndev) { set_error("bsfm_match_all_pairs_multi: ngpus = %d but %d device(s) are visible", ngpus, ndev); return BSFM_ERR_ARG; }
+    if (ngpus == 1 && !devices) return bsfm_match_all_pairs(keys, key_off, num_images, window_radius, ratio, pair_counts, pair_cap, matches, match_cap);
+    MultiShared S;
+    S.keys = keys; S.key_off = key_off; S.N = num_images; S.window = window_radius; S.ratio = ratio; S.ngpus = ngpus; S.devices = devices;
+    S.pair_counts = pair_counts; S.pair_cap = pair_cap; S.matches = matches; S.match_cap = match_cap;
+    S.result.assign((size_t) ngpus, BSFM_ERR_CUDA); S.errors.assign((size_t) ngpus, std::string()); S.search_ms.assign((size_t) ngpus, 0.f);
+    int saved = 0;
+    cudaGetDevice(&saved);
+    int rc = bsfm_comm_unique_id(S.id);
+    if (rc != BSFM_OK) return rc;
+    std::vector<std::thread> threads;
+    for (int r = 0; r < ngpus; r++) threads.emplace_back(multi_worker, &S, r);     // one host thread per GPU
+    for (auto &t : threads) t.join();
+    cudaSetDevice(saved);
+    for (int r = 0; r < ngpus; r++)
+        if (S.result[(size_t) r] < 0) { set_error("bsfm_match_all_pairs_multi: rank %d: %s", r, S.errors[(size_t) r].c_str()); return S.result[(size_t) r]; }
+    return S.result[0];
 }
 
 /* releases the device images bsfm_match_pair keeps between calls */

@@ -27,11 +27,14 @@ __global__ void raw_norm_kernel(const uint8_t *__restrict__ raw, int64_t total_k
 __global__ void prep_kernel(const uint8_t *__restrict__ raw, const int64_t *__restrict__ key_off,
                             const int32_t *__restrict__ img_doff, const int32_t *__restrict__ tile_img,
                             const int32_t *__restrict__ sorted_src, const int32_t *__restrict__ sorted_norms,
-                            uint8_t *__restrict__ keys_sw, int32_t *__restrict__ norms, int32_t *__restrict__ perm, int64_t drows)
+                            uint8_t *__restrict__ keys_sw, int32_t *__restrict__ norms, int32_t *__restrict__ perm,
+                            int64_t row_begin, int64_t row_end, int64_t key_base)
 {
-    int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // rows [row_begin, row_end) of the device layout; `raw`, `sorted_src`, `sorted_norms` hold the keys [key_base, ...) only
+    // (a rank of a sharded build prepares its own images; key_base = 0 and the whole row range otherwise)
+    int64_t row = row_begin + (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
-    if (row >= drows) return;
+    if (row >= row_end) return;
     int img = tile_img[row >> 7];
     uint32_t w = 0;
     int32_t nrm = NORM_PAD, orig = -1;
@@ -39,11 +42,11 @@ __global__ void prep_kernel(const uint8_t *__restrict__ raw, const int64_t *__re
         int64_t k = row - img_doff[img];
         int64_t n = key_off[img + 1] - key_off[img];
         if (k < n) {
-            const int64_t srow = sorted_src[key_off[img] + k];
+            const int64_t srow = sorted_src[key_off[img] - key_base + k];      // row inside `raw`
             const uint8_t *src = raw + srow * DESC_BYTES + lane * 4;
             w = (uint32_t) src[0] | ((uint32_t) src[1] << 8) | ((uint32_t) src[2] << 16) | ((uint32_t) src[3] << 24);
-            nrm = sorted_norms[key_off[img] + k];
-            orig = (int32_t) (srow - key_off[img]);
+            nrm = sorted_norms[key_off[img] - key_base + k];
+            orig = (int32_t) (srow + key_base - key_off[img]);
         }
     }
     int c = lane >> 2;  // 16-byte chunk

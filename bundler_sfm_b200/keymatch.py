@@ -57,14 +57,59 @@ def pair_list(num_images, window_radius=-1, img_begin=0, img_end=None):
     return [(j, i) for i in range(img_begin, img_end) for j in range(start_image(i, window_radius), i)]
 
 
-class KeyDatabase:
-    """Device-resident descriptors of all images (uploaded once, KeyMatchFull.cpp:93-99)."""
+COMM_ID_BYTES = 128
 
-    def __init__(self, keys, key_off, device_ptr=None):
+
+class Comm:
+    """One rank of the library's NCCL communicator (bsfm_comm).  `from_torch()` ships rank 0's unique id through the
+    torch.distributed process group the caller already has (one process per GPU); `Comm(id, rank, world)` is the raw form."""
+
+    def __init__(self, uid, rank, world):
+        self._lib = load_library()
+        self.rank, self.world = int(rank), int(world)
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.shape == (COMM_ID_BYTES,)
+        self._h = self._lib.bsfm_comm_create(uid.ctypes.data, self.rank, self.world)
+        if not self._h:
+            check(-1, "bsfm_comm_create")
+
+    @staticmethod
+    def unique_id():
+        uid = np.zeros(COMM_ID_BYTES, np.uint8)
+        check(load_library().bsfm_comm_unique_id(uid.ctypes.data), "bsfm_comm_unique_id")
+        return uid
+
+    @classmethod
+    def from_torch(cls, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        t = torch.from_numpy(cls.unique_id() if rank == 0 else np.zeros(COMM_ID_BYTES, np.uint8))
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=0, group=group)
+        return cls(t.cpu().numpy(), rank, world)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bsfm_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class KeyDatabase:
+    """Device-resident descriptors of all images (uploaded once, KeyMatchFull.cpp:93-99).  With `comm` the database is built
+    cooperatively: every rank prepares 1/world of the images and the prepared rows are all-gathered over NVLink."""
+
+    def __init__(self, keys, key_off, device_ptr=None, comm=None):
         self._lib = load_library()
         self.key_off = np.ascontiguousarray(key_off, dtype=np.int64)
         self.num_images = len(self.key_off) - 1
-        if device_ptr is not None:
+        if comm is not None:
+            keys = np.ascontiguousarray(keys, dtype=np.uint8)
+            self._h = self._lib.bsfm_keydb_create_sharded(comm._h, keys.ctypes.data, self.key_off.ctypes.data, self.num_images)
+        elif device_ptr is not None:
             self._h = self._lib.bsfm_keydb_create_dev(ctypes.c_void_p(device_ptr), self.key_off.ctypes.data, self.num_images)
         else:
             keys = np.ascontiguousarray(keys, dtype=np.uint8)
@@ -94,6 +139,20 @@ class KeyDatabase:
         check(self._lib.bsfm_match_fetch(self._h, counts.ctypes.data, counts.shape[0], matches.ctypes.data, matches.shape[0]),
               "bsfm_match_fetch")
         return counts[:npairs], matches[:n_m.value]
+
+    def allgather(self, comm):
+        """NCCL all-gather of the ranks' tables inside the library (bsfm_match_allgather) -> total matches"""
+        return check(self._lib.bsfm_match_allgather(comm._h, self._h), "bsfm_match_allgather")
+
+    def gathered_fetch(self):
+        """(pair_counts, matches) of the gathered table on the host"""
+        n_p, n_m = ctypes.c_int64(), ctypes.c_int64()
+        check(self._lib.bsfm_match_gathered_fetch(self._h, ctypes.byref(n_p), ctypes.byref(n_m), None, 0, None, 0), "bsfm_match_gathered_fetch")
+        counts = np.zeros(max(n_p.value, 1), dtype=np.int32)
+        matches = np.zeros((max(n_m.value, 1), 2), dtype=np.int32)
+        check(self._lib.bsfm_match_gathered_fetch(self._h, None, None, counts.ctypes.data, counts.shape[0], matches.ctypes.data, matches.shape[0]),
+              "bsfm_match_gathered_fetch")
+        return counts[:n_p.value], matches[:n_m.value]
 
     def result_dev(self):
         """(pair_counts_ptr, num_pairs, matches_ptr, num_matches) -- device pointers for NCCL."""
@@ -129,6 +188,35 @@ def key_match_full(keys_list, window_radius=-1, ratio=0.6):
     finally:
         db.close()
     return pair_list(len(keys_list), window_radius), counts, matches
+
+
+def shard_range(key_off, window_radius, world_size, rank):
+    """the library's own split (bsfm_match_shard_range; same rule as shard_images)"""
+    key_off = np.ascontiguousarray(key_off, dtype=np.int64)
+    b, e = ctypes.c_int(), ctypes.c_int()
+    check(load_library().bsfm_match_shard_range(key_off.ctypes.data, len(key_off) - 1, window_radius, world_size, rank, ctypes.byref(b), ctypes.byref(e)),
+          "bsfm_match_shard_range")
+    return b.value, e.value
+
+
+def key_match_full_multi(keys_list, window_radius=-1, ratio=0.6, ngpus=2, devices=None):
+    """bsfm_match_all_pairs_multi: the whole pair loop on `ngpus` devices of this process (one host thread per GPU,
+    NCCL all-gather of prepared descriptors and of the match table) -> (pairs, counts, matches)"""
+    lib = load_library()
+    keys, key_off = concat_keys(keys_list)
+    npairs = lib.bsfm_match_num_pairs(len(keys_list), window_radius)
+    counts = np.zeros(max(npairs, 1), np.int32)
+    cap = int(sum(k.shape[0] for k in keys_list)) * 4 + 1024
+    dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+    while True:
+        matches = np.zeros((cap, 2), np.int32)
+        total = lib.bsfm_match_all_pairs_multi(keys.ctypes.data, key_off.ctypes.data, len(keys_list), window_radius, float(ratio), ngpus,
+                                               None if dev is None else dev.ctypes.data, counts.ctypes.data, counts.shape[0], matches.ctypes.data, cap)
+        if total == -4 and cap < (1 << 30):      # BSFM_ERR_CAPACITY: grow and retry
+            cap *= 4
+            continue
+        check(total, "bsfm_match_all_pairs_multi")
+        return pair_list(len(keys_list), window_radius), counts[:npairs], matches[:total]
 
 
 def format_match_table(pairs, counts, matches, min_matches=16):

@@ -33,6 +33,8 @@ const char *bsfm_version(void);
 int64_t bsfm_kernel_launches(void);
 /* select the CUDA device used by subsequent calls of this thread's process (default: current) */
 int bsfm_set_device(int device);
+/* number of CUDA devices visible to this process (0 when there is none) */
+int bsfm_device_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * MATCH
@@ -119,6 +121,32 @@ int64_t bsfm_match_all_pairs(const uint8_t *keys, const int64_t *key_off, int nu
 /* ------------------------------------------------------------------------------------------------
  * BA  (declared in bsfm_b200_ba.h; kept separate because it mirrors the reference structs)
  * ---------------------------------------------------------------------------------------------- */
+
+/* ---- multi-GPU: the KeyMatchFull pair loop (src/KeyMatchFull.cpp:105-151) sharded by database image, one
+ * communicator rank per GPU, NCCL over NVLink.  Works with one process per GPU (the id travels through whatever launcher
+ * the caller has: bench.py broadcasts it with torch.distributed) and with several host threads in one process.
+ * NCCL (libnccl.so.2) is bound at run time; without it these entry points return BSFM_ERR_UNSUPPORTED.               */
+typedef struct bsfm_comm bsfm_comm;
+#define BSFM_COMM_ID_BYTES 128
+int bsfm_comm_unique_id(unsigned char id[BSFM_COMM_ID_BYTES]);                                /* rank 0: ncclGetUniqueId */
+bsfm_comm *bsfm_comm_create(const unsigned char id[BSFM_COMM_ID_BYTES], int rank, int world_size);   /* on the CURRENT device */
+void bsfm_comm_destroy(bsfm_comm *comm);
+/* cooperative bsfm_keydb_create: rank r uploads and prepares (norm sort + swizzle) only its 1/world share of the images;
+ * the prepared rows are exchanged with one in-place ncclAllGather per array; every rank ends with the whole database.
+ * Collective: every rank of `comm` must call it with the same arguments.                                            */
+bsfm_keydb *bsfm_keydb_create_sharded(bsfm_comm *comm, const uint8_t *keys, const int64_t *key_off, int num_images);
+/* contiguous database-image range of `rank`: equal shares of the work n_i * sum_{j in window} n_j                    */
+int bsfm_match_shard_range(const int64_t *key_off, int num_images, int window_radius, int world_size, int rank, int *img_begin, int *img_end);
+/* all-gather of the ranks' tables after each ran bsfm_match_run on its range (ranges in rank order): count all-gather,
+ * then one grouped broadcast per rank into its offset of the concatenated table (== the KeyMatchFull order).  Collective.
+ * Returns the total number of matches; the table stays in device memory of every rank.                               */
+int64_t bsfm_match_allgather(bsfm_comm *comm, bsfm_keydb *db);
+/* gathered table -> host or device buffers (*num_pairs / *num_matches = sizes of the whole table; null buffers: sizes only) */
+int bsfm_match_gathered_fetch(bsfm_keydb *db, int64_t *num_pairs, int64_t *num_matches, int32_t *pair_counts, int64_t pair_cap, int32_t *matches, int64_t match_cap);
+/* bsfm_match_all_pairs on `ngpus` devices of this process (one host thread per GPU; devices == NULL: 0 .. ngpus-1):
+ * the export SURVEY.md 8b names for the multi-GPU KeyMatchFull.  Same outputs as bsfm_match_all_pairs.               */
+int64_t bsfm_match_all_pairs_multi(const uint8_t *keys, const int64_t *key_off, int num_images, int window_radius, double ratio,
+                                   int ngpus, const int *devices, int32_t *pair_counts, int64_t pair_cap, int32_t *matches, int64_t match_cap);
 
 #ifdef __cplusplus
 }

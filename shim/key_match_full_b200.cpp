@@ -110,25 +110,32 @@ int main(int argc, char **argv)
         if (num_keys[i] > 0) memcpy(all.data() + (size_t) key_off[i] * 128, keys[i], (size_t) num_keys[i] * 128);
     for (int i = 0; i < num_images; i++) delete[] keys[i];                         // KeyMatchFull.cpp:154-157
 
-    bsfm_keydb *db = bsfm_keydb_create(all.data(), key_off.data(), num_images);
-    if (db == NULL) {
-        printf("[KeyMatchFull/b200] error: %s\n", bsfm_last_error());
-        return EXIT_FAILURE;
+    // every visible GPU takes a contiguous share of the database images (BSFM_MATCH_GPUS overrides the count): the library
+    // shards the key-database build and the pair loop and all-gathers the table over NCCL (bsfm_match_all_pairs_multi)
+    int ngpus = 1;
+    {
+        const char *e = getenv("BSFM_MATCH_GPUS");
+        const int visible = bsfm_device_count();
+        ngpus = e ? atoi(e) : visible;
+        if (ngpus < 1) ngpus = 1;
+        if (visible > 0 && ngpus > visible) ngpus = visible;
+        if (ngpus > num_images) ngpus = std::max(1, num_images);
     }
-    const int64_t total = bsfm_match_run(db, 0, num_images, window_radius, ratio);
+    const int64_t npairs = bsfm_match_num_pairs(num_images, window_radius);
+    std::vector<int32_t> pair_counts((size_t) std::max<int64_t>(npairs, 1));
+    std::vector<int32_t> matches;
+    int64_t total = 0;
+    for (int64_t cap = std::max<int64_t>(key_off[num_images], 1024);; cap *= 4) {      // grows on BSFM_ERR_CAPACITY
+        matches.assign((size_t) cap * 2, 0);
+        total = bsfm_match_all_pairs_multi(all.data(), key_off.data(), num_images, window_radius, ratio, ngpus, NULL,
+                                           pair_counts.data(), npairs, matches.data(), cap);
+        if (total != BSFM_ERR_CAPACITY || cap > ((int64_t) 1 << 33)) break;
+    }
     if (total < 0) {
         printf("[KeyMatchFull/b200] error %lld: %s\n", (long long) total, bsfm_last_error());
         return EXIT_FAILURE;
     }
-    const int64_t npairs = bsfm_match_shard_pairs(db);
-    std::vector<int32_t> pair_counts((size_t) std::max<int64_t>(npairs, 1));
-    std::vector<int32_t> matches((size_t) std::max<int64_t>(total, 1) * 2);
-    const int rc = bsfm_match_fetch(db, pair_counts.data(), npairs, matches.data(), total);
-    if (rc != BSFM_OK) {
-        printf("[KeyMatchFull/b200] error %d: %s\n", rc, bsfm_last_error());
-        return EXIT_FAILURE;
-    }
-    bsfm_keydb_destroy(db);
+    printf("[KeyMatchFull/b200] %d GPU(s)\n", ngpus);
     printf("[KeyMatchFull] Matching took %0.3fs\n", now_s() - t0);
     fflush(stdout);
 

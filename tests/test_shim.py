@@ -207,8 +207,8 @@ def test_sba_motstr_levmar_reference_signature_program(tmp_path, oracle):
     assert abs(np.sqrt(info[1] / nvis) - np.sqrt(ref["info"][1] / nvis)) <= 1e-5
     assert info[7] == ref["info"][7] and info[8] == ref["info"][8]      # simple driver scales nfev / njev by nvis (sba_levmar_wrap.c:684-695)
     got = bundle.unpack_params(p, scene)
-    for key in ("R", "c", "f", "pts"):
-        err = np.max(np.linalg.norm((got[key] - ref[key]).reshape(len(ref[key]), -1), axis=1) / np.maximum(np.linalg.norm(np.asarray(ref[key]).reshape(len(ref[key]), -1), axis=1), 1e-12))
+    for key in ("R", "c", "f", "pts"):       # the parameter gate of tests/test_ba_gpu.py (relative to the group's scale)
+        err = float(np.max(np.abs(got[key] - ref[key])) / np.max(np.abs(ref[key])))
         assert err <= 1e-4, (key, err)
     # a foreign projection callback is refused loudly with SBA_ERROR (no CPU fallback)
     r = subprocess.run([exe, "foreign"], capture_output=True, text=True)
@@ -233,4 +233,4 @@ def test_sba_mot_levmar_reference_signature_program(tmp_path, oracle):
     got = bundle.unpack_params(p, scene)
     assert np.array_equal(got["pts"], np.asarray(scene["pts"], float))          # points untouched
     for key in ("c", "f"):
-        assert np.max(np.abs(got[key] - ref[key]) / np.maximum(np.abs(ref[key]), 1e-9)) <= 1e-4, key
+        assert float(np.max(np.abs(got[key] - ref[key])) / np.max(np.abs(ref[key]))) <= 1e-4, key

@@ -80,6 +80,41 @@ def load_library():
     return lib
 
 
+_NCCL_PRELOADED = False
+
+
+def preload_nccl():
+    """The library binds NCCL at run time with dlopen("libnccl.so.2").  Inside a Python process that also imports torch the
+    copy that must answer is the one torch ships (nvidia/nccl/lib): if the system libnccl.so.2 were loaded first under the
+    same SONAME, torch's own import would later resolve against it and fail on symbols newer than the system copy.
+    So: load torch's copy first when there is one (found without importing torch); BSFM_NCCL_LIB overrides the path."""
+    global _NCCL_PRELOADED
+    if _NCCL_PRELOADED:
+        return
+    _NCCL_PRELOADED = True
+    import importlib.util
+    cands = []
+    if os.environ.get("BSFM_NCCL_LIB"):
+        cands.append(os.environ["BSFM_NCCL_LIB"])
+    for mod in ("nvidia.nccl", "torch"):
+        try:
+            spec = importlib.util.find_spec(mod)
+        except (ImportError, ValueError):
+            spec = None
+        if spec is None:
+            continue
+        for base in (list(spec.submodule_search_locations or []) or [os.path.dirname(spec.origin or "")]):
+            cands.append(os.path.join(base, "lib", "libnccl.so.2"))
+            cands.append(os.path.join(os.path.dirname(base), "nvidia", "nccl", "lib", "libnccl.so.2"))
+    for path in cands:
+        if path and os.path.exists(path):
+            try:
+                ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                return
+            except OSError:
+                continue
+
+
 def last_error():
     return load_library().bsfm_last_error().decode()
 

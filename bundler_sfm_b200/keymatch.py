@@ -10,7 +10,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import load_library, check
+from ._lib import load_library, check, preload_nccl
 
 DESC_DIM = 128
 
@@ -65,6 +65,7 @@ class Comm:
     torch.distributed process group the caller already has (one process per GPU); `Comm(id, rank, world)` is the raw form."""
 
     def __init__(self, uid, rank, world):
+        preload_nccl()
         self._lib = load_library()
         self.rank, self.world = int(rank), int(world)
         uid = np.ascontiguousarray(uid, dtype=np.uint8)
@@ -75,6 +76,7 @@ class Comm:
 
     @staticmethod
     def unique_id():
+        preload_nccl()
         uid = np.zeros(COMM_ID_BYTES, np.uint8)
         check(load_library().bsfm_comm_unique_id(uid.ctypes.data), "bsfm_comm_unique_id")
         return uid
@@ -202,6 +204,7 @@ def shard_range(key_off, window_radius, world_size, rank):
 def key_match_full_multi(keys_list, window_radius=-1, ratio=0.6, ngpus=2, devices=None):
     """bsfm_match_all_pairs_multi: the whole pair loop on `ngpus` devices of this process (one host thread per GPU,
     NCCL all-gather of prepared descriptors and of the match table) -> (pairs, counts, matches)"""
+    preload_nccl()
     lib = load_library()
     keys, key_off = concat_keys(keys_list)
     npairs = lib.bsfm_match_num_pairs(len(keys_list), window_radius)

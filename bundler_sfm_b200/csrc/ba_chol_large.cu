@@ -465,13 +465,37 @@ int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *li
     const bool use_tc = ws && ws->slices && tc_syrk_available();
     static const bool diag_prof = getenv("BSFM_DIAG_PROF") != nullptr;
     if (diag_prof && !g_diag_dbg) { cudaMalloc(&g_diag_dbg, 8 * sizeof(long long)); cudaMemset(g_diag_dbg, 0, 8 * sizeof(long long)); }
+    // Look-ahead (tensor-core path): the diagonal block of panel p+1 is a ~0.15 ms serial chain on ONE SM.  The trailing update
+    // of panel p is therefore split into the two tile columns panel p+1 lives in (launched first) and the rest, and
+    // diag(p+1) runs on a side stream next to the rest, which leaves it one SM (grid = SMs - 1):
+    //   main : trsm(p)  col(p) -E1->  rest(p) ............ -wait E2->  trsm(p+1) ...
+    //   side :                 wait E1  diag(p+1) -E2->
+    // BSFM_BA_CHOL_LOOKAHEAD=0 serialises everything on the main stream (also the fp64 DMMA fallback).
+    static const bool lookahead_env = []() { const char *e = getenv("BSFM_BA_CHOL_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+    const bool lookahead = use_tc && lookahead_env;
+    struct SideStream { int device = -1; cudaStream_t st = nullptr; cudaEvent_t e_col = nullptr, e_diag = nullptr; };
+    static thread_local SideStream side;
+    if (lookahead && side.device != dev) {
+        if (side.st) { cudaStreamDestroy(side.st); cudaEventDestroy(side.e_col); cudaEventDestroy(side.e_diag); side = SideStream(); }
+        BSFM_CUDA_TRY(cudaStreamCreateWithFlags(&side.st, cudaStreamNonBlocking));
+        BSFM_CUDA_TRY(cudaEventCreateWithFlags(&side.e_col, cudaEventDisableTiming));
+        BSFM_CUDA_TRY(cudaEventCreateWithFlags(&side.e_diag, cudaEventDisableTiming));
+        side.device = dev;
+    }
+    const int sms = tc_sm_count();
+    bool diag_done = false;       // diag(p) already issued by the look-ahead of panel p-1
     for (int k0 = 0; k0 < n; k0 += LNBO) {
         const int nb = std::min(LNBO, n - k0);
         const int k1 = k0 + nb;
-        g_prof.begin(0, st);
-        chol_diag_kernel<<<1, DG_THREADS, DG_SMEM_DOUBLES * sizeof(double), st>>>(A, Lmat, ld, n, k0, linv_ws, sc, k0 == 0 ? g_diag_dbg : nullptr);
-        BSFM_KERNEL_CHECK();
-        g_prof.end(st);
+        if (!diag_done) {
+            g_prof.begin(0, st);
+            chol_diag_kernel<<<1, DG_THREADS, DG_SMEM_DOUBLES * sizeof(double), st>>>(A, Lmat, ld, n, k0, linv_ws, sc, k0 == 0 ? g_diag_dbg : nullptr);
+            BSFM_KERNEL_CHECK();
+            g_prof.end(st);
+        } else {
+            BSFM_CUDA_TRY(cudaStreamWaitEvent(st, side.e_diag, 0));
+        }
+        diag_done = false;
         const int rows_below = nrows - k1;     // >= 1: the right-hand side row
         SliceOut so = {};
         if (use_tc && k1 < n) so = tc_slice_out(*ws, k1, n);
@@ -488,7 +512,20 @@ int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *li
                 g_prof.fp64_flops += 2.0 * pairs * nb;
                 if (use_tc) g_prof.int8_ops += 2.0 * pairs * nb * (ws->ns * (ws->ns + 1) / 2);
             }
-            if (use_tc) {
+            if (use_tc && lookahead) {
+                const int col_tiles = LNBO / TC_TILE;      // the tile columns of the next panel
+                int rc = tc_syrk_update(st, *ws, A, Lmat, ld, nrows, k1, n, k0, k1, 0, col_tiles, 0);
+                if (rc != BSFM_OK) return rc;
+                BSFM_CUDA_TRY(cudaEventRecord(side.e_col, st));
+                BSFM_CUDA_TRY(cudaStreamWaitEvent(side.st, side.e_col, 0));
+                chol_diag_kernel<<<1, DG_THREADS, DG_SMEM_DOUBLES * sizeof(double), side.st>>>(A, Lmat, ld, n, k1, linv_ws, sc, nullptr);
+                BSFM_KERNEL_CHECK();
+                BSFM_CUDA_TRY(cudaEventRecord(side.e_diag, side.st));
+                diag_done = true;
+                if (g_prof.on) g_prof.launches[0]++;
+                rc = tc_syrk_update(st, *ws, A, Lmat, ld, nrows, k1, n, k0, k1, col_tiles, -1, std::max(1, sms - 1));
+                if (rc != BSFM_OK) return rc;
+            } else if (use_tc) {
                 int rc = tc_syrk_update(st, *ws, A, Lmat, ld, nrows, k1, n, k0, k1);
                 if (rc != BSFM_OK) return rc;
             } else {
@@ -500,6 +537,7 @@ int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *li
             g_prof.end(st);
         }
     }
+    if (diag_done) BSFM_CUDA_TRY(cudaStreamWaitEvent(st, side.e_diag, 0));
     g_prof.begin(3, st);
     // L_pp^-T of every panel at once (the panel solve applied to the rows of the identity), then the back substitution
     const int npan = (n + LNBO - 1) / LNBO;

@@ -47,7 +47,11 @@ bool tc_syrk_available();
 int tc_slices_wanted();
 inline SliceOut tc_slice_out(const TcWorkspace &ws, int, int) { SliceOut so; so.slices = ws.slices; so.rscale = ws.rscale; so.ns = ws.ns; return so; }
 // A[r][c] -= sum_{t in [kb,ke)} L[r][t] L[c][t]  for c in [cb,ce), r in [c, nrows)  from the slices of panel [kb,ke)
-int tc_syrk_update(cudaStream_t st, const TcWorkspace &ws, double *A, const double *L, int ld, int nrows, int cb, int ce, int kb, int ke);
+// restricted to the 128-column tile columns [col_tile_begin, col_tile_end) of the trailing matrix (end < 0: all) on at most
+// `max_ctas` CTAs (0: one per SM)
+int tc_syrk_update(cudaStream_t st, const TcWorkspace &ws, double *A, const double *L, int ld, int nrows, int cb, int ce, int kb, int ke,
+                   int col_tile_begin = 0, int col_tile_end = -1, int max_ctas = 0);
+int tc_sm_count();
 int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *xinv_ws, double *x, Scalars *sc, const TcWorkspace *ws);
 // doubles of linear-solver workspace behind the 32 x 32 inverses: back-substitution scratch (small path) or the 256 x 256 panel inverses (large path)
 inline size_t chol_extra_ws_doubles(int n) { return (size_t) ((n + LNBO - 1) / LNBO) * LNBO * LNBO + (size_t) n + 64; }

@@ -43,6 +43,7 @@ struct TcSyrkParams {
     double *A;
     int ns, ld, nrows, cb, ce;
     int tile0, nct, ntiles;
+    int nrt, tc0, tc1;          // row tiles; tile columns [tc0, tc1) of this launch (column-major enumeration inside the range)
     unsigned long long *prof;   // dev-only cycle accounting of CTA 0 (BSFM_TCS_PROF=1), else null
 };
 // prof[0..3] MMA thread: wait slices, wait accumulator stage, issue, levels;  [4..5] producer: wait slot, loads;
@@ -50,18 +51,13 @@ struct TcSyrkParams {
 #define TCS_T(var) const long long var = P.prof ? clock64() : 0
 #define TCS_ADD(i, v) do { if (P.prof && blockIdx.x == 0) atomicAdd(&P.prof[i], (unsigned long long) (v)); } while (0)
 
-__device__ __forceinline__ void tcs_decode_tile(int idx, int nct, int &ti, int &tj)
+// tile idx of a launch -> (row tile ti, column tile tj): columns tc0 .. tc1-1 one after the other, rows tj .. nrt-1 inside
+// a column (lower triangle).  Column-major order keeps the column tile's slices hot in L2 for consecutive CTAs.
+__device__ __forceinline__ void tcs_decode_tile(int idx, const TcSyrkParams &P, int &ti, int &tj)
 {
-    const int tri = nct * (nct + 1) / 2;
-    if (idx < tri) {
-        int t = (int) ((sqrtf(8.0f * (float) idx + 1.0f) - 1.0f) * 0.5f);
-        while (t * (t + 1) / 2 > idx) t--;
-        while ((t + 1) * (t + 2) / 2 <= idx) t++;
-        ti = t; tj = idx - t * (t + 1) / 2;
-    } else {
-        const int rem = idx - tri;
-        ti = nct + rem / nct; tj = rem % nct;
-    }
+    int c = P.tc0;
+    while (idx >= P.nrt - c) { idx -= P.nrt - c; c++; }
+    tj = c; ti = c + idx;
 }
 
 // UMMA instruction descriptor, kind::i8: c S32 (2) [4,6), a/b format [7,10)/[10,13) 0 = u8, 1 = s8, K-major,
@@ -149,7 +145,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_syrk_kernel(const TcSyrkPar
             uint32_t it = 0;      // running (tile, K-half) counter: slot phase = it & 1
             for (int idx = blockIdx.x; idx < P.ntiles; idx += gridDim.x) {
                 int ti, tj;
-                tcs_decode_tile(idx, P.nct, ti, tj);
+                tcs_decode_tile(idx, P, ti, tj);
                 if ((P.ld & 1) == 0) {
                     // the fp64 tile this CTA will read-modify-write ~25 us from now: pull its 128 rows (1 KB each) into L2 so
                     // that the write-back of all CTAs (they run in lockstep) does not hit HBM in one burst
@@ -217,7 +213,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_syrk_kernel(const TcSyrkPar
         uint32_t q = 0;
         for (int idx = blockIdx.x; idx < P.ntiles; idx += gridDim.x) {
             int ti, tj;
-            tcs_decode_tile(idx, P.nct, ti, tj);
+            tcs_decode_tile(idx, P, ti, tj);
             double acc[32];
 #pragma unroll
             for (int j = 0; j < 32; j++) acc[j] = 0.0;
@@ -294,6 +290,12 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tc_syrk_kernel(const TcSyrkPar
 }
 
 static unsigned long long *g_tcs_prof = nullptr;
+int tc_sm_count()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return sms;
+}
 bool tc_syrk_available()
 {
     static const bool on = []() { const char *e = getenv("BSFM_BA_TC"); return !(e && e[0] == '0'); }();
@@ -309,7 +311,8 @@ int tc_slices_wanted()
     return ns;
 }
 
-int tc_syrk_update(cudaStream_t st, const TcWorkspace &ws, double *A, const double *, int ld, int nrows, int cb, int ce, int kb, int ke)
+int tc_syrk_update(cudaStream_t st, const TcWorkspace &ws, double *A, const double *, int ld, int nrows, int cb, int ce, int kb, int ke,
+                   int col_tile_begin, int col_tile_end, int max_ctas)
 {
     if (ke - kb != LNBO || (cb % TC_TILE) != 0 || ws.ns < 1 || ws.ns > TCS_NS_MAX) { set_error("tc_syrk_update: unsupported panel geometry"); return BSFM_ERR_ARG; }
     int dev = 0;
@@ -327,11 +330,16 @@ int tc_syrk_update(cudaStream_t st, const TcWorkspace &ws, double *A, const doub
     TcSyrkParams P;
     P.slices = ws.slices; P.rscale = ws.rscale; P.A = A; P.ns = ws.ns; P.ld = ld; P.nrows = nrows; P.cb = cb; P.ce = ce;
     P.tile0 = cb / TC_TILE;
-    const int nrt = (nrows - cb + TC_TILE - 1) / TC_TILE;
+    P.nrt = (nrows - cb + TC_TILE - 1) / TC_TILE;
     P.nct = (ce - cb + TC_TILE - 1) / TC_TILE;
-    P.ntiles = P.nct * (P.nct + 1) / 2 + (nrt - P.nct) * P.nct;
+    P.tc0 = std::max(0, col_tile_begin);
+    P.tc1 = (col_tile_end < 0) ? P.nct : std::min(P.nct, col_tile_end);
+    if (P.tc0 >= P.tc1) return BSFM_OK;
+    P.ntiles = 0;
+    for (int c = P.tc0; c < P.tc1; c++) P.ntiles += P.nrt - c;
     const int sms = (dev >= 0 && dev < 64) ? sm_count[dev].load() : 148;
-    const int grid = std::min(P.ntiles, sms > 0 ? sms : 148);
+    int grid = std::min(P.ntiles, sms > 0 ? sms : 148);
+    if (max_ctas > 0) grid = std::min(grid, max_ctas);
     static unsigned long long *d_prof = []() -> unsigned long long * {
         if (!getenv("BSFM_TCS_PROF")) return nullptr;
         unsigned long long *q = nullptr;

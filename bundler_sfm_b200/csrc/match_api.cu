@@ -288,7 +288,7 @@ static int grow_matches(bsfm_keydb *db, int64_t need)
     return BSFM_OK;
 }
 
-static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int window_radius, double ratio)
+static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int window_radius, double ratio, int test_mode = 0)
 {
     clear_error();
     if (!db) { set_error("bsfm_match_run: null db"); return BSFM_ERR_ARG; }
@@ -374,7 +374,11 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     MatchParams P;
     P.keys_sw = db->d_keys_sw; P.norms = db->d_norms; P.run_imgs = d_run; P.num_run_imgs = K;
     P.perm = db->d_perm; P.tile_img = db->d_tile_img; P.img_doff = db->d_img_doff;
-    P.ratio_sq = ratio * ratio;
+    // test mode 1 (keys.cpp:786): final decisions evaluate sqrt(d0 / d1) <= ratio on exact distances; the bound pre-filters,
+    // which may only defer, use a slightly inflated ratio^2 so that rounding in the division / sqrt can never reject a match
+    P.test_mode = test_mode;
+    P.ratio = ratio;
+    P.ratio_sq = (test_mode == 0) ? ratio * ratio : ratio * ratio * (1.0 + 1e-9);
     P.neg2 = -2;
     P.cand = (int32_t *) (S + o_cand); P.cand_cap = (int32_t) cap;
     P.hard = (int32_t *) (S + o_hard);
@@ -685,7 +689,7 @@ int ensure_pair_db(PairCache &C, int64_t rows, int device)
     return BSFM_OK;
 }
 
-int match_pair_cached(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int32_t *out_pairs, int cap)
+int match_pair_cached(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int test_mode, int32_t *out_pairs, int cap)
 {
     PairCache &C = g_pair_cache;
     std::lock_guard<std::mutex> lock(C.mu);
@@ -719,7 +723,7 @@ int match_pair_cached(const uint8_t *k1, int n1, const uint8_t *k2, int n2, doub
     BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_norms + rows_a, b->d_norms, rb * 4, cudaMemcpyDeviceToDevice, st));
     BSFM_CUDA_TRY(cudaMemcpyAsync(db->d_perm + rows_a, b->d_perm, rb * 4, cudaMemcpyDeviceToDevice, st));
     BSFM_CUDA_TRY(cudaStreamSynchronize(st));      // tile_img is a host temporary
-    int64_t total = match_run_impl(db, 1, 2, -1, ratio);
+    int64_t total = match_run_impl(db, 1, 2, -1, ratio, test_mode);
     if (total < 0) return (int) total;
     if (total > 0) {
         std::vector<int32_t> m((size_t) total * 2);
@@ -736,12 +740,18 @@ int match_pair_cached(const uint8_t *k1, int n1, const uint8_t *k2, int n2, doub
 extern "C" {
 int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int32_t *out_pairs, int cap)
 {
+    return bsfm_match_pair_test(k1, n1, k2, n2, ratio, BSFM_RATIO_TEST_KEYS2A, out_pairs, cap);
+}
+
+int bsfm_match_pair_test(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int ratio_test, int32_t *out_pairs, int cap)
+{
     clear_error();
     if (n1 < 0 || n2 < 0 || cap < 0) { set_error("bsfm_match_pair: negative size"); return BSFM_ERR_ARG; }
+    if (ratio_test != BSFM_RATIO_TEST_KEYS2A && ratio_test != BSFM_RATIO_TEST_KEYS) { set_error("bsfm_match_pair_test: unknown ratio test %d", ratio_test); return BSFM_ERR_ARG; }
     int rc = require_device();
     if (rc != BSFM_OK) return rc;
     if (n1 == 0 || n2 == 0) return 0;
-    if (env_int("BSFM_MATCH_PAIR_CACHE", 1) != 0) return match_pair_cached(k1, n1, k2, n2, ratio, out_pairs, cap);
+    if (env_int("BSFM_MATCH_PAIR_CACHE", 1) != 0 || ratio_test != BSFM_RATIO_TEST_KEYS2A) return match_pair_cached(k1, n1, k2, n2, ratio, ratio_test, out_pairs, cap);
     std::vector<uint8_t> keys((size_t) (n1 + n2) * DESC_BYTES);
     memcpy(keys.data(), k1, (size_t) n1 * DESC_BYTES);
     memcpy(keys.data() + (size_t) n1 * DESC_BYTES, k2, (size_t) n2 * DESC_BYTES);

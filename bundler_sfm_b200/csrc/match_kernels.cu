@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) match_dp4a_kernel(MatchParams P)
             if (na >= NORM_PAD_HALF) continue;  // padding query row
             const int d0 = na + m1[a];
             const int d1 = (m2[a] >= NORM_PAD_HALF) ? INT_MAX : na + m2[a];
-            if ((double) d0 < P.ratio_sq * (double) d1) {
+            if (ratio_pass(P, d0, d1)) {
                 int pos = atomicAdd(&P.counters[1], 1);
                 if (pos < P.match_cap) {
                     P.match_slot[pos] = match_sort_key(P, R, a_row0 + r);
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
         if (f6 == INT_MIN) {
             // exact mode: d0 = m1 is the global minimum, f5 bounds d1 from above through the other chunks
             const int d1 = min(f5, m2);
-            match = (double) m1 < P.ratio_sq * (double) d1;
+            match = ratio_pass(P, m1, d1);
         } else {
             // bound mode: the chunk with the smallest lower bound was recomputed exactly (m1, m2).  It holds the
             // global minimum iff m1 <= every other chunk's lower bound; d1 lies in [min(m2, L2), min(m2, Uo)].
@@ -706,8 +706,8 @@ __global__ void __launch_bounds__(256) match_verify_kernel(MatchParams P, int nc
             if (m1 > l2d) hard = true;
             else {
                 const int d1_low = min(m2, l2d), d1_up = min(m2, uod);
-                if ((double) m1 < P.ratio_sq * (double) d1_low) match = true;
-                else if ((double) m1 < P.ratio_sq * (double) d1_up) hard = true;   // undecided inside the bound slack
+                if (ratio_pass(P, m1, d1_low)) match = true;
+                else if (ratio_pass(P, m1, d1_up)) hard = true;   // undecided inside the bound slack
             }
         }
         if (hard) {
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(256) match_fullscan_kernel(MatchParams P, int 
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int q = 1; q < 8; q++) merge(s_m1[q], s_m2[q], s_mi[q]);
-        if ((double) m1 < P.ratio_sq * (double) m2) {
+        if (ratio_pass(P, m1, m2)) {
             int pos = atomicAdd(&P.counters[1], 1);
             if (pos < P.match_cap) { P.match_slot[pos] = match_sort_key(P, R, qrow); P.match_idx2[pos] = mi; }
             else P.counters[2] = 1;

@@ -78,7 +78,11 @@ struct MatchParams {
     int32_t num_run_imgs;
     int32_t unit_begin;         // units [unit_begin, unit_end) are processed by this launch
     int32_t unit_end;
-    double ratio_sq;            // ratio*ratio evaluated on the host in double (keys2a.cpp:362)
+    double ratio_sq;            // ratio*ratio evaluated on the host in double (keys2a.cpp:362); test mode 1: inflated by 1e-9
+                                // (only the conservative pre-filters of the tensor-core epilogue read it there)
+    double ratio;               // the ratio itself (test mode 1)
+    int32_t test_mode;          // 0: (double) d0 < ratio^2 (double) d1          MatchKeys of keys2a.cpp:362 / :412
+                                // 1: sqrt((double) d0 / (double) d1) <= ratio   MatchKeys of keys.cpp:786 (bundler --add_images)
     int32_t neg2;               // the constant -2 as a runtime value (see the epilogue of match_tc_kernel)
     int32_t epi_mode;           // 1 = bound epilogue (max tree on norm-sorted chunks), 0 = exact chunk minima
     // candidate list (tensor-core kernel): SoA int32 [7][cand_cap]: slot, qrow, db0, col0, nvalid, f5, f6
@@ -92,6 +96,14 @@ struct MatchParams {
     int32_t match_cap;
     int32_t *counters;          // [0] = #candidates, [1] = #matches, [2] = overflow flag, [3] = #hard rows
 };
+
+// the ratio test on an exact (d0, d1) pair -- or on bounds of d1: both forms are monotone in d1, so a test that passes with a
+// lower bound of d1 passes with d1 itself
+__device__ __forceinline__ bool ratio_pass(const MatchParams &P, int d0, int d1)
+{
+    if (P.test_mode == 0) return (double) d0 < P.ratio_sq * (double) d1;
+    return sqrt((double) d0 / (double) d1) <= P.ratio;       // 0 / 0 = NaN: no match, as in the reference
+}
 
 // byte offset of 16-byte chunk c (0..7) of device row r in the swizzled layout
 __host__ __device__ __forceinline__ size_t sw_chunk_offset(int64_t row, int c)

@@ -63,6 +63,17 @@ int bsfm_device_count(void);
  * only the first cap are written and the full count is still returned.                       */
 int bsfm_match_pair(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio,
                     int32_t *out_pairs, int cap);
+/* The same 2-NN search with a selectable acceptance test:
+ *   BSFM_RATIO_TEST_KEYS2A  (double) d0 < ratio^2 (double) d1           MatchKeys of src/keys2a.cpp:362, :412 (KeyMatchFull)
+ *   BSFM_RATIO_TEST_KEYS    sqrt((double) d0 / (double) d1) <= ratio    MatchKeys / MatchKeysExhaustive of src/keys.cpp:786, :1029
+ *                           (bundler --add_images, src/Bundle.cpp:3812-3820; d1 = INT_MAX when image 2 has one key)
+ * Exact search, i.e. keys.cpp's MatchKeysExhaustive (the stock MatchKeys there caps the kd-tree search at 200 visits).
+ * For ratio >= 1 the partner reported for a query whose two nearest keys are EXACTLY equidistant is the one with the
+ * smaller index (the reference reports whichever its kd-tree meets first).                                             */
+#define BSFM_RATIO_TEST_KEYS2A 0
+#define BSFM_RATIO_TEST_KEYS   1
+int bsfm_match_pair_test(const uint8_t *k1, int n1, const uint8_t *k2, int n2, double ratio, int ratio_test,
+                         int32_t *out_pairs, int cap);
 /* bsfm_match_pair keeps the prepared device image of every key buffer it has seen (keyed by key count and a 64-bit hash
  * of the contents; the unmodified KeyMatchFull main passes the same buffers for every pair, KeyMatchFull.cpp:105-151),
  * least recently used images are dropped beyond 8 GB.  This releases them all.                                       */

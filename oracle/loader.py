@@ -45,6 +45,8 @@ def port():
         c = ctypes
         _port.oracle_match_pair.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_int, c.c_double, c.c_void_p, c.c_int]
         _port.oracle_match_pair.restype = c.c_int
+        _port.oracle_match_pair_test.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_int, c.c_double, c.c_int, c.c_void_p, c.c_int]
+        _port.oracle_match_pair_test.restype = c.c_int
         _port.oracle_top2_all.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p]
         _port.oracle_top2_all.restype = None
         _port.oracle_match_all_pairs.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_double, c.c_int,
@@ -70,6 +72,57 @@ def ref_match():
         lib.ref_match_tree.restype = c.c_int
         _ref_match = lib
     return _ref_match
+
+
+_ref_keys = None
+
+
+def ref_keys():
+    """reference in-bundler matcher (src/keys.cpp + ann_1.1_char), or None when oracle/_ref was not built"""
+    global _ref_keys
+    if _ref_keys is None:
+        lib = _load(os.path.join(_HERE, "_ref", "libref_keys.so"))
+        if lib is None:
+            return None
+        c = ctypes
+        lib.ref_keys_match.argtypes = [c.c_int, c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_double, c.c_int, c.c_void_p, c.c_int]
+        lib.ref_keys_match.restype = c.c_int
+        _ref_keys = lib
+    return _ref_keys
+
+
+def keys_match_ref(k1, k2, extra2=None, registered=False, ratio=0.6, exhaustive=True, fn=None):
+    """MatchKeysExhaustive / MatchKeys of src/keys.cpp through the doorway (or the same-shaped `fn` of the shim)"""
+    if fn is None:
+        lib = ref_keys()
+        assert lib is not None, "oracle/_ref/libref_keys.so not built"
+        fn = lib.ref_keys_match
+    k1, k2 = _u8(k1), _u8(k2)
+    ex = None if extra2 is None else np.ascontiguousarray(extra2, dtype=np.int32)
+    out = np.empty((max(k1.shape[0], 1), 2), np.int32)
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 1); os.close(devnull)   # "[MatchKeys] Found ..." chatter
+    try:
+        n = fn(k1.shape[0], k1.ctypes.data, k2.shape[0], k2.ctypes.data, None if ex is None else ex.ctypes.data, int(bool(registered)),
+               float(ratio), int(bool(exhaustive)), out.ctypes.data, out.shape[0])
+    finally:
+        os.dup2(saved, 1); os.close(saved)
+    return out[:n].copy()
+
+
+def match_pair_port_test(k1, k2, ratio, mode, extra2=None, registered=False):
+    """the C restatement with the selectable acceptance test (mode 1 = keys.cpp) and the `registered` subset"""
+    k1, k2 = _u8(k1), _u8(k2)
+    sel = np.arange(k2.shape[0])
+    if registered:
+        sel = np.nonzero(np.asarray(extra2) >= 0)[0]
+    db = np.ascontiguousarray(k2[sel])
+    out = np.empty((max(k1.shape[0], 1), 2), np.int32)
+    n = port().oracle_match_pair_test(k1.ctypes.data, k1.shape[0], db.ctypes.data, db.shape[0], float(ratio), int(mode), out.ctypes.data, out.shape[0])
+    res = out[:n].copy()
+    res[:, 1] = sel[res[:, 1]] if n else res[:, 1]
+    return res
 
 
 def ref_sba():

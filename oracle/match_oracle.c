@@ -18,6 +18,7 @@
  * pass for ratio<=1 (KeyMatchFull hard-codes 0.6), so index tie-breaking is unobservable.
  */
 #include <limits.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -61,6 +62,26 @@ int oracle_match_pair(const unsigned char *k1, int n1, const unsigned char *k2, 
         int d0, d1, i0, i1;
         oracle_top2(k1 + (size_t) DESC_DIM * i, k2, n2, &d0, &d1, &i0, &i1);
         if (((double) d0) < ratio * ratio * ((double) d1)) {   /* keys2a.cpp:362 */
+            if (cnt < cap) { out_pairs[2 * cnt] = i; out_pairs[2 * cnt + 1] = i0; }
+            cnt++;
+        }
+    }
+    return cnt;
+}
+
+/* The in-bundler matcher, src/keys.cpp:961-1057 (MatchKeysExhaustive; MatchKeys :717-810 is the same loop on an approximate
+ * search): accept iff sqrt((double) d0 / (double) d1) <= ratio (:786, :1029).  mode 0 = the keys2a test above.
+ * (`registered` is applied by the caller: it only selects which keys of image 2 form the database.) */
+int oracle_match_pair_test(const unsigned char *k1, int n1, const unsigned char *k2, int n2,
+                           double ratio, int mode, int32_t *out_pairs, int cap)
+{
+    int cnt = 0, i;
+    if (mode == 0) return oracle_match_pair(k1, n1, k2, n2, ratio, out_pairs, cap);
+    if (n1 <= 0 || n2 <= 0) return 0;
+    for (i = 0; i < n1; i++) {
+        int d0, d1, i0, i1;
+        oracle_top2(k1 + (size_t) DESC_DIM * i, k2, n2, &d0, &d1, &i0, &i1);
+        if (sqrt(((double) d0) / ((double) d1)) <= ratio) {
             if (cnt < cap) { out_pairs[2 * cnt] = i; out_pairs[2 * cnt + 1] = i0; }
             cnt++;
         }

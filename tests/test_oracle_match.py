@@ -89,3 +89,20 @@ def test_all_pairs_table_format(oracle):
     # windowed variant only visits j >= i - window
     txt_w, counts_w = oracle.match_all_pairs_port(imgs, 1, 0.6, 16)
     assert counts_w[3, 0] == 0 and counts_w[3, 2] == counts[3, 2]
+
+
+def test_port_keys_cpp_test_mode_vs_reference_exhaustive():
+    """oracle/match_oracle.c mode 1 (sqrt(d0/d1) <= ratio, `registered` subset) against the UNMODIFIED MatchKeysExhaustive of
+    src/keys.cpp (oracle/_ref/libref_keys.so): the pair of calls bundler --add_images makes (Bundle.cpp:3812-3820)"""
+    from oracle import loader
+    if loader.ref_keys() is None:
+        pytest.skip("oracle/_ref/libref_keys.so not built")
+    imgs = synth.sift_like_descriptors(2, [600, 750], seed=11)
+    extra = np.where(np.random.default_rng(3).random(750) < 0.6, 5, -1).astype(np.int32)
+    for reg, ratio in ((True, 0.75), (False, 1.0), (False, 0.6), (True, 0.9)):
+        want = loader.keys_match_ref(imgs[0], imgs[1], extra, reg, ratio, exhaustive=True)
+        got = loader.match_pair_port_test(imgs[0], imgs[1], ratio, 1, extra, reg)
+        assert np.array_equal(got, want), (reg, ratio)
+        assert want.shape[0] > 0
+    # (a database of ONE key is a fatal error in the reference: ANN aborts with "Requesting more near neighbors than data
+    #  points", lib/ann_1.1_char/src/kd_search.cpp -- not a case to compare)

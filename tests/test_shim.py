@@ -234,3 +234,48 @@ def test_sba_mot_levmar_reference_signature_program(tmp_path, oracle):
     assert np.array_equal(got["pts"], np.asarray(scene["pts"], float))          # points untouched
     for key in ("c", "f"):
         assert float(np.max(np.abs(got[key] - ref[key])) / np.max(np.abs(ref[key]))) <= 1e-4, key
+
+
+# ------------------------------------------------------------------------------------------------
+# (f)4: MatchKeys(std::vector<KeypointWithDesc>...) of src/keys.cpp (bundler --add_images) -> GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_keys_cpp_matchkeys_overload_equals_reference_exhaustive(oracle):
+    """shim/keys_b200.cpp (compiled against the reference's keys.h) against the unmodified MatchKeysExhaustive, for the two
+    calls BundleRegisterImage makes (registered / 0.75 and unregistered / 1.0, Bundle.cpp:3812-3820) and more"""
+    so = os.path.join(BUILD, "libkeys_b200.so")
+    if not os.path.exists(so) or oracle.ref_keys() is None:
+        pytest.skip("needs shim/_build/libkeys_b200.so and oracle/_ref/libref_keys.so")
+    bundle.load_library()
+    shim = ctypes.CDLL(so).shim_keys_match
+    shim.argtypes = oracle.ref_keys().ref_keys_match.argtypes
+    shim.restype = ctypes.c_int
+    imgs = synth.sift_like_descriptors(3, [1800, 2300, 1], seed=12)
+    extra = np.where(np.random.default_rng(4).random(2300) < 0.5, 7, -1).astype(np.int32)
+    for reg, ratio in ((True, 0.75), (False, 1.0), (False, 0.6), (True, 0.95)):
+        want = oracle.keys_match_ref(imgs[0], imgs[1], extra, reg, ratio, exhaustive=True)
+        for exhaustive in (True, False):      # both names are exact on the GPU
+            got = oracle.keys_match_ref(imgs[0], imgs[1], extra, reg, ratio, exhaustive=exhaustive, fn=shim)
+            assert np.array_equal(got, want), (reg, ratio, exhaustive)
+        assert want.shape[0] > 0
+    # a database of one key aborts the reference (ANN: "Requesting more near neighbors than data points"); here d1 = INT_MAX
+    # (ANN_DIST_INF) and every query matches it, like MatchKeys of keys2a.cpp does.  An empty registered set gives no match.
+    assert oracle.keys_match_ref(imgs[0][:50], imgs[2], None, False, 0.75, fn=shim).shape[0] == 50
+    none = np.full(2300, -1, np.int32)
+    assert oracle.keys_match_ref(imgs[0][:50], imgs[1], none, True, 0.75, fn=shim).shape[0] == 0
+
+
+@pytest.mark.gpu
+def test_match_pair_test_modes_vs_port(oracle):
+    lib = bundle.load_library()
+    fn = lib.bsfm_match_pair_test
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    fn.restype = ctypes.c_int
+    imgs = synth.sift_like_descriptors(2, [900, 1100], seed=13)
+    for mode in (0, 1):
+        for ratio in (0.6, 0.9, 1.0):
+            out = np.zeros((900, 2), np.int32)
+            n = fn(imgs[0].ctypes.data, 900, imgs[1].ctypes.data, 1100, ratio, mode, out.ctypes.data, 900)
+            want = oracle.match_pair_port_test(imgs[0], imgs[1], ratio, mode)
+            assert n == want.shape[0] and np.array_equal(out[:n], want), (mode, ratio)
+    assert fn(imgs[0].ctypes.data, 900, imgs[1].ctypes.data, 1100, 0.6, 7, None, 0) < 0     # unknown test

@@ -41,6 +41,34 @@ WORKLOAD_STR = {
 METRIC_STR = {"ba": "LM iterations/s (sparse bundle adjustment solve)", "match": "descriptor-pairs/s (all-pairs SIFT match, KeyMatchFull)"}
 
 
+def measure_device_peaks(torch, dev):
+    """measured on THIS box, in this process, before the timed runs (each takes a few tens of ms):
+      int8 tensor pipe : a plain tcgen05.mma kind::i8 loop of the library (bsfm_measure_int8_peak; N = 256 and N = 128 tiles)
+      fp64             : cuBLAS DGEMM through torch.matmul, 6144^3, best of 5"""
+    from bundler_sfm_b200 import _lib
+    lib = _lib.load_library()
+    out = {}
+    try:
+        out["int8_tops_n256"] = max(lib.bsfm_measure_int8_peak(256, 20000) for _ in range(2))
+        out["int8_tops_n128"] = max(lib.bsfm_measure_int8_peak(128, 40000) for _ in range(2))
+    except Exception as e:      # noqa: BLE001 -- never fake a peak
+        out["int8_error"] = str(e)
+    try:
+        n = 6144
+        a = torch.randn(n, n, dtype=torch.float64, device=dev)
+        b = torch.randn(n, n, dtype=torch.float64, device=dev)
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); c = a @ b; e1.record(); torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out["fp64_dgemm_tflops"] = best
+        del a, b, c
+    except Exception as e:      # noqa: BLE001
+        out["fp64_error"] = str(e)
+    return out
+
+
 def usable_cores():
     """host cores this process may really use: the scheduler affinity mask, capped by the cgroup CPU quota"""
     try:
@@ -561,7 +589,14 @@ def main():
     args.warmup = max(args.warmup, 3)
     peaks = load_peaks()
     wl = pick_workload(args)
-    i8_peak = 2.0 * peaks["bf16_tflops"]
+    dpk = measure_device_peaks(torch, dev)
+    if dpk.get("int8_tops_n256", 0) > 0:
+        i8_peak = dpk["int8_tops_n256"]
+        i8_src = ("measured on this GPU by a plain tcgen05.mma kind::i8 loop (M128 N256, operands resident in shared memory; "
+                  f"N128 tiles reach {dpk.get('int8_tops_n128', 0):.0f}); 2 x bf16 dense of MEASURED_PEAKS.json would be {2.0 * peaks['bf16_tflops']:.0f}")
+    else:
+        i8_peak = 2.0 * peaks["bf16_tflops"]
+        i8_src = "2 x bf16 dense, " + peaks["source"]
 
     def ba_object(ba, key):
         """the BA fields of a JSON line (headline or side object)"""
@@ -578,8 +613,10 @@ def main():
                                "frac": c["trailing_int8_tops"] / i8_peak, "traffic": None,
                                "kernel": "tc_syrk_kernel (tcgen05 kind::i8 int8-slice trailing update of the reduced-camera Cholesky)",
                                "fp64_equivalent_tflops": c["trailing_fp64_equiv_tflops"],
+                               "fp64_dgemm_tflops_measured": dpk.get("fp64_dgemm_tflops"),
                                "note": "dominant kernel of the solve; achieved = algorithmic int8 ops (28 slice products x 2 x lower-triangle MACs) / CUDA-event "
-                                       "time of its launches in one solve; peak = 2 x bf16 dense, " + peaks["source"]}
+                                       "time of its launches in one solve; fp64_equivalent_tflops = the same update counted as fp64 FLOPs, next to this "
+                                       "GPU's cuBLAS DGEMM rate; peak = " + i8_src}
             obj["cholesky_kernels"] = c
         else:
             obj["roofline"] = {"bound": "hbm", "achieved": ba["roofline_achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -596,7 +633,7 @@ def main():
                 "gpu_launches": match["launches"], "clocks": match["clocks"],
                 "roofline": {"bound": "tensor", "achieved": match["int8_tops_search_kernel"], "peak": i8_peak, "unit": "TOP/s (int8)",
                              "frac": match["int8_tops_search_kernel"] / i8_peak, "traffic": None,
-                             "note": "tcgen05 kind::i8 search kernel per GPU; 256 int8 ops per descriptor pair; peak = 2 x bf16 dense, " + peaks["source"]},
+                             "note": "tcgen05 kind::i8 search kernel per GPU; 256 int8 ops per descriptor pair; peak = " + i8_src},
                 "match_detail": match}
 
     line, cpu = None, None
@@ -632,6 +669,7 @@ def main():
         head.update({k: v for k, v in line.items() if k not in head})
         if cpu is not None:
             head["cpu_baseline"] = cpu
+        head["measured_peaks_this_run"] = dpk
         print(json.dumps(head), flush=True)
     if dist is not None:
         dist.destroy_process_group()

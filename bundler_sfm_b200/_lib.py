@@ -76,6 +76,8 @@ def load_library():
                                                c.c_void_p, c.c_int64, c.c_void_p, c.c_int64]
     lib.bsfm_match_all_pairs_multi.restype = c.c_int64
     lib.bsfm_match_pair_cache_clear.restype = None
+    lib.bsfm_measure_int8_peak.argtypes = [c.c_int, c.c_int]
+    lib.bsfm_measure_int8_peak.restype = c.c_double
     _LIB = lib
     return lib
 

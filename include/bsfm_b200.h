@@ -33,6 +33,10 @@ const char *bsfm_version(void);
 int64_t bsfm_kernel_launches(void);
 /* select the CUDA device used by subsequent calls of this thread's process (default: current) */
 int bsfm_set_device(int device);
+/* Measured int8 tensor-pipe ceiling of the current device in TOP/s (2 ops per multiply-add): a plain tcgen05.mma kind::i8
+ * loop, M = 128, N = n_tile (128 or 256), operands resident in shared memory, no loads, no epilogue (csrc/tc_peak.cu).
+ * bench.py uses it as the denominator of the tensor rooflines.  < 0 on error.                        */
+double bsfm_measure_int8_peak(int n_tile, int iters);
 /* number of CUDA devices visible to this process (0 when there is none) */
 int bsfm_device_count(void);
 

@@ -1,8 +1,8 @@
 // tc_peak.cu -- measured int8 tensor-pipe ceiling of this GPU: a plain tcgen05.mma kind::i8 loop ("measure
 // peak with a plain tcgen05 i8 GEMM on the same box").  One CTA per SM; one thread issues back-to-back MMAs
-// (M = 128, N = 128 or 256, K = 4 x 32 per tile) on operand tiles that stay resident in shared memory (pseudo-random
-// bytes, K-major SWIZZLE_128B like the real kernels), alternating between two TMEM accumulator stages; no loads, no
-// epilogue.  What it reports is the rate the MATCH search kernel (N = 256) and the BA trailing update (N = 128) are
+// (M = 128, N = 128 or 256, K = 4 x 32 per tile) on operand tiles resident in shared memory -- a ring of four (A, B) tile
+// pairs of pseudo-random bytes, K-major SWIZZLE_128B like the real kernels, so consecutive tiles read different operands --
+// alternating between two TMEM accumulator stages; no loads, no epilogue.  What it reports is the rate the MATCH search kernel (N = 256) and the BA trailing update (N = 128) are
 // measured against (bench.py roofline.peak); it is an upper bound for any kernel built from the same instruction shape.
 #include "common.h"
 #include "tc_ptx.cuh"
@@ -17,9 +17,10 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int n_tile)
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw_addr);
-    const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 16384 + 32768 + 16);
-    for (int q = threadIdx.x; q < (16384 + 32768) / 4; q += blockDim.x) {      // pseudo-random operand bytes
+    constexpr int STAGES = 4, STAGE_BYTES = 16384 + 32768;      // ring of (A 128 x 128 B, B 256 x 128 B) tiles, as a pipelined GEMM keeps
+    const uint32_t bar = base + STAGES * STAGE_BYTES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + STAGES * STAGE_BYTES + 16);
+    for (int q = threadIdx.x; q < STAGES * STAGE_BYTES / 4; q += blockDim.x) {      // pseudo-random operand bytes
         uint32_t v = (uint32_t) q * 2654435761u + blockIdx.x * 40503u;
         v ^= v >> 15; v *= 2246822519u; v ^= v >> 13;
         reinterpret_cast<uint32_t *>(smem)[q] = v;
@@ -35,13 +36,16 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int n_tile)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) {
-        const uint64_t adesc = make_sw128_desc(sA), bdesc = make_sw128_desc(sB);
+        uint64_t adesc[STAGES], bdesc[STAGES];
+#pragma unroll
+        for (int st = 0; st < STAGES; st++) { adesc[st] = make_sw128_desc(base + st * STAGE_BYTES); bdesc[st] = make_sw128_desc(base + st * STAGE_BYTES + 16384); }
         const uint32_t idesc = (2u << 4) | ((uint32_t) (n_tile >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);      // u8 x u8 -> s32
         uint32_t phase = 0;
         for (int it = 0; it < iters; it++) {
             const uint32_t tmem_d = tmem_base + (uint32_t) (it & 1) * 256;
+            const uint64_t ad = adesc[it & (STAGES - 1)], bd = bdesc[it & (STAGES - 1)];      // every tile reads different operands
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) tc_mma_i8(tmem_d, adesc + (uint64_t) (kk * 2), bdesc + (uint64_t) (kk * 2), idesc, kk > 0);
+            for (int kk = 0; kk < 4; kk++) tc_mma_i8(tmem_d, ad + (uint64_t) (kk * 2), bd + (uint64_t) (kk * 2), idesc, kk > 0);
             if ((it & 15) == 15 || it == iters - 1) {      // bound the number of MMAs in flight
                 tc_commit(bar);
                 mbar_wait(bar, phase);
@@ -65,7 +69,7 @@ extern "C" double bsfm_measure_int8_peak(int n_tile, int iters)
     if ((n_tile != 128 && n_tile != 256) || iters < 16) { set_error("bsfm_measure_int8_peak: n_tile must be 128 or 256, iters >= 16"); return -1.0; }
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { set_error("device query failed"); return -1.0; }
-    const size_t smem = 16384 + 32768 + 64 + 1024;
+    const size_t smem = 4 * (16384 + 32768) + 64 + 1024;
     if (cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); return -1.0; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -602,8 +602,8 @@ def main():
         """the BA fields of a JSON line (headline or side object)"""
         obj = {"metric": METRIC_STR["ba"], "value": ba["value"], "unit": "LM iterations/s", "steps": ba["steps"], "warmup": ba["warmup"],
                "ms_per_step": ba["ms_per_step"], "dtype": "f64",
-               "config": {"workload": WORKLOAD_STR[key] + "; N>1 = N independent replicas (BA does not shard); L2 flushed between timed steps (256 MB buffer)",
-                          **BA_CFGS[key], "jacobian": "finite-difference (reference-compatible)", "lm_iterations_per_solve": ba["iterations_per_solve"],
+               "config": {"workload": WORKLOAD_STR[key], **BA_CFGS[key],
+                          "note": "N>1 = N independent replicas (BA does not shard); L2 flushed between timed steps (256 MB buffer)", "jacobian": "finite-difference (reference-compatible)", "lm_iterations_per_solve": ba["iterations_per_solve"],
                           "final_rmse_px": ba["rmse"]},
                "e2e": {"value": ba["e2e_value"], "unit": "LM iterations/s", "h2d_bytes_per_step": ba["h2d"], "d2h_bytes_per_step": ba["d2h"]},
                "gpu_launches": ba["launches"], "clocks": ba["clocks"], "ba_phase_ms_one_solve": ba["phase_ms"]}
@@ -627,7 +627,7 @@ def main():
     def match_object(match):
         return {"metric": METRIC_STR["match"], "value": match["desc_pairs_per_s"], "unit": "descriptor-pairs/s",
                 "steps": match["steps"], "warmup": match["warmup"], "ms_per_step": match["ms_per_pass"], "dtype": "u8",
-                "config": {"workload": WORKLOAD_STR["match"] + "; descriptors (320 MB) exceed L2", **MATCH_CFG},
+                "config": {"workload": WORKLOAD_STR["match"], **MATCH_CFG, "note": "descriptors (320 MB) exceed L2"},
                 "e2e": {"value": match["e2e_desc_pairs_per_s"], "unit": "descriptor-pairs/s", "h2d_bytes_per_step": match["h2d_bytes"],
                         "d2h_bytes_per_step": match["matches"] * 8},
                 "gpu_launches": match["launches"], "clocks": match["clocks"],

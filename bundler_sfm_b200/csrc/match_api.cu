@@ -800,12 +800,16 @@ bsfm_comm *bsfm_comm_create(const unsigned char id[BSFM_COMM_ID_BYTES], int rank
     memcpy(&u, id, sizeof u);
     ncclResult_t r = nc.CommInitRank(&c->comm, world_size, u, rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", nc.GetErrorString(r)); delete c; return nullptr; }
-    // first collective of a communicator sets up its channels (tens of ms): pay that here, not inside the first timed call
+    // the first collectives of a communicator set up its channels and, for large messages, its bulk-protocol buffers (tens to
+    // hundreds of ms): pay that here with one small and one 4 MB-per-rank all-gather, not inside the first real call
     if (world_size > 1) {
+        const size_t per = (size_t) 1 << 20;
         int32_t *d = nullptr;
-        if (cudaMalloc(&d, (size_t) world_size * sizeof(int32_t)) == cudaSuccess) {
-            cudaMemset(d, 0, (size_t) world_size * sizeof(int32_t));
+        if (cudaMalloc(&d, (size_t) world_size * per * sizeof(int32_t)) == cudaSuccess) {
+            cudaMemset(d, 0, (size_t) world_size * per * sizeof(int32_t));
             nc.AllGather(d + rank, d, 1, ncclInt32, c->comm, (cudaStream_t) 0);
+            nc.AllGather(d + rank * per, d, per, ncclInt32, c->comm, (cudaStream_t) 0);
+            nc.Broadcast(d, d, 1024, ncclInt32, 0, c->comm, (cudaStream_t) 0);
             cudaStreamSynchronize((cudaStream_t) 0);
             cudaFree(d);
         }

@@ -509,8 +509,13 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
             e2e_parts = {"database_build_ms": 1e3 * (t1 - t0), "search_ms": 1e3 * (t2 - t1), "table_allgather_ms": 1e3 * (t3 - t2), "fetch_ms": 1e3 * (t4 - t3)}
         e2e_matches = int(m_host.shape[0])
     t = torch.tensor([dev_ms * 1e-3, search_ms * 1e-3, e2e_wall, wall], dtype=torch.float64, device=dev)
+    parts_all = [e2e_parts]
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pt = torch.tensor([e2e_parts[k] for k in ("database_build_ms", "search_ms", "table_allgather_ms", "fetch_ms")], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(pt) for _ in range(world)]
+        dist.all_gather(gathered, pt)
+        parts_all = [dict(zip(("database_build_ms", "search_ms", "table_allgather_ms", "fetch_ms"), [round(float(x), 2) for x in g.tolist()])) for g in gathered]
     dev_s, search_s, e2e_wall, wall = t[0].item(), t[1].item(), t[2].item(), t[3].item()
     npairs = num_images * (num_images - 1) // 2
     dp = float(npairs) * keys_per_image * keys_per_image
@@ -522,7 +527,7 @@ def bench_match(args, torch, dist, rank, world, dev, num_images, keys_per_image,
             "wall_ms_per_pass": 1e3 * wall / steps, "launches": int(launches), "clocks": clocks,
             "search_kernel_ms_per_pass_max_rank": 1e3 * search_s / steps, "int8_tops_search_kernel": dp * 256 / world / (search_s / steps) / 1e12,
             "e2e_desc_pairs_per_s": dp / e2e_wall, "matches": int(total_matches), "h2d_bytes": int(keys.nbytes), "images": num_images, "keys_per_image": keys_per_image,
-            "pairs": npairs, "shard": [int(b), int(e)], "steps": steps, "warmup": warmup, "e2e_breakdown_ms_rank0": e2e_parts}
+            "pairs": npairs, "shard": [int(b), int(e)], "steps": steps, "warmup": warmup, "e2e_breakdown_ms_per_rank": parts_all}
 
 
 def cpu_baseline_ba2():

@@ -22,6 +22,7 @@ __global__ void prep_kernel(const uint8_t *, const int64_t *, const int32_t *, c
 __global__ void match_dp4a_kernel(MatchParams);
 __global__ void match_tc_kernel(MatchParams);
 __global__ void match_tc_bound_kernel(MatchParams);
+__global__ void match_tc_quad_kernel(MatchParams);
 __global__ void match_tc_pair_kernel(MatchParams);
 __global__ void match_verify_kernel(MatchParams, int);
 __global__ void match_fullscan_kernel(MatchParams, int);
@@ -120,6 +121,9 @@ struct bsfm_comm {
     int rank = 0, world = 1, device = 0;
 };
 
+#ifndef BSFM_MATCH_QUAD_DEFAULT
+#define BSFM_MATCH_QUAD_DEFAULT 0
+#endif
 static int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -389,6 +393,8 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     // cta_group::2 kernel (CTA pairs, half the L2 -> SM traffic) vs one CTA per unit (default: measured faster, the
     // path is bound by the TMEM -> register read of the epilogue, not by L2)
     const bool pair_mode = env_int("BSFM_MATCH_PAIR", 0) != 0;
+    // four accumulator stages of 128 columns (match_tc_quad_kernel) instead of two of 256
+    const bool quad_mode = env_int("BSFM_MATCH_QUAD", BSFM_MATCH_QUAD_DEFAULT) != 0;
     P.match_slot = (uint32_t *) (S + o_slot_a); P.match_idx2 = (int32_t *) (S + o_idx_a); P.match_cap = (int32_t) cap;
     P.counters = (int32_t *) (S + o_cnt);
 
@@ -397,6 +403,7 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
     if (db->device < 0 || db->device >= 64 || !attr_done[db->device].load(std::memory_order_acquire)) {
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
+        BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         BSFM_CUDA_TRY(cudaFuncSetAttribute(match_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_ALLOC));
         if (db->device >= 0 && db->device < 64) attr_done[db->device].store(1, std::memory_order_release);
     }
@@ -432,7 +439,8 @@ static int64_t match_run_impl(bsfm_keydb *db, int img_begin, int img_end, int wi
                 attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
                 BSFM_CUDA_TRY(cudaLaunchKernelEx(&cfg, match_tc_pair_kernel, P));
-            } else if (P.epi_mode == 1) match_tc_bound_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
+            } else if (P.epi_mode == 1 && quad_mode) match_tc_quad_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
+            else if (P.epi_mode == 1) match_tc_bound_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
             else match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_ALLOC, db->stream>>>(P);
             BSFM_KERNEL_CHECK();
             BSFM_CUDA_TRY(cudaEventRecord(db->ev[2], db->stream));

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256) match_dp4a_kernel(MatchParams P)
 
 using namespace bsfm::ptx;   // tc_ptx.cuh
 constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t) (TILE_DB >> 3) << 17) | ((uint32_t) (TILE_Q >> 4) << 24);
+constexpr uint32_t TC_IDESC_N128 = (2u << 4) | ((uint32_t) (128 >> 3) << 17) | ((uint32_t) (TILE_Q >> 4) << 24);
 constexpr uint32_t TC_IDESC_PAIR = (2u << 4) | ((uint32_t) (TILE_DB >> 3) << 17) | ((uint32_t) ((2 * TILE_Q) >> 4) << 24);
 // 3-input MAX (VIMNMX3) over the 32 values of a chunk and `init`: four independent chains
 __device__ __forceinline__ int chunk_max(const uint32_t (&v)[32], int init)
@@ -260,9 +261,16 @@ extern "C" int bsfm_debug_prof(unsigned long long *out)
 // PAIR  = true : two CTAs of a cluster (an SM pair) issue ONE cta_group::2 MMA per database tile: M = 256 (128
 //                query rows per CTA), every CTA stages only HALF of the 256-row database tile, which halves the
 //                L2 -> SM traffic per MAC (the single-CTA kernel is L2-bandwidth bound, profiles/r1_match_tc_v6).
-template <bool BOUND, bool PAIR>
+// QUAD = true : (bound epilogue, single CTA) FOUR accumulator stages of 128 columns instead of two of 256: every 256-row
+//                database tile is issued as two N = 128 MMAs groups into consecutive stages and the 16 epilogue warps form four
+//                groups, one per stage.  The stage hand-over (MMA -> commit -> epilogue wake-up -> TMEM loads -> release -> MMA)
+//                costs ~650 cycles on top of the loads; with four stages in flight twice as many hand-overs overlap.
+template <bool BOUND, bool PAIR, bool QUAD = false>
 __device__ __forceinline__ void match_tc_body(const MatchParams &P)
 {
+    static_assert(!QUAD || (BOUND && !PAIR), "the four-stage variant exists for the bound epilogue on single CTAs");
+    constexpr int NTS = QUAD ? 4 : 2;                 // accumulator stages
+    constexpr int TS_COLS = QUAD ? 128 : TILE_DB;     // TMEM columns per stage
     extern __shared__ uint8_t smem_raw[];
     // manual 1024-byte alignment (SWIZZLE_128B atoms)
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -280,10 +288,10 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
     const uint32_t bar_b_empty = bar0 + 8 * BST;               // [BST]
     const uint32_t bar_a_full = bar0 + 16 * BST;               // [2]
     const uint32_t bar_a_empty = bar_a_full + 16;              // [2]
-    const uint32_t bar_t_full = bar_a_empty + 16;              // [2]
-    const uint32_t bar_t_empty = bar_t_full + 16;              // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_SMEM_BAR + 8 * (2 * BST + 8));
-    static_assert(8 * (2 * BST + 8) + 4 <= 256, "barrier region");
+    const uint32_t bar_t_full = bar_a_empty + 16;              // [NTS]
+    const uint32_t bar_t_empty = bar_t_full + 8 * NTS;         // [NTS]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_SMEM_BAR + 8 * (2 * BST + 4 + 2 * NTS));
+    static_assert(8 * (2 * BST + 4 + 2 * NTS) + 4 <= 256, "barrier region");
     const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
 
     const int warp = threadIdx.x >> 5;
@@ -297,9 +305,11 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_a_full + 8 * s, full_cnt);
             mbar_init(bar_a_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < NTS; s++) {
             mbar_init(bar_t_full + 8 * s, 1);
             // bound mode: one warp group per stage; pair: one arrival per warp of the group in both CTAs
-            mbar_init(bar_t_empty + 8 * s, !BOUND ? TC_EPI_THREADS : (PAIR ? 2 : 1) * TC_EPI_WARPS / 2);
+            mbar_init(bar_t_empty + 8 * s, QUAD ? TC_EPI_WARPS / 4 : (!BOUND ? TC_EPI_THREADS : (PAIR ? 2 : 1) * TC_EPI_WARPS / 2));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -390,6 +400,21 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                     PROF_T(q2);
                     tc_fence_after();
                     const uint64_t bdesc = make_sw128_desc(sB + bs * BSLOT);
+                    if constexpr (QUAD) {
+                        // rows 0..127 and 128..255 of the database tile into two consecutive 128-column stages
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {
+                            if (half) { mbar_wait(bar_t_empty + 8 * ts, tph ^ 1); tc_fence_after(); }
+                            const uint32_t tmem_d = tmem_base + ts * TS_COLS;
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++)      // second half: +128 rows x 128 B = +1024 in the descriptor start field
+                                tc_mma_i8(tmem_d, adesc + (uint64_t) (kk * 2), bdesc + (uint64_t) (half * 1024 + kk * 2), TC_IDESC_N128, kk > 0);
+                            if (half) tc_commit(bar_b_empty + 8 * bs);
+                            tc_commit(bar_t_full + 8 * ts);
+                            ts = (ts + 1) & 3; if (ts == 0) tph ^= 1;
+                        }
+                        if (++bs == BST) { bs = 0; bph ^= 1; }
+                    } else {
                     const uint32_t tmem_d = tmem_base + ts * TILE_DB;
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) {  // K = 4 x 32 bytes; +32 B = +2 in the descriptor start field
@@ -400,6 +425,7 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                     else { tc_commit(bar_b_empty + 8 * bs); tc_commit(bar_t_full + 8 * ts); }
                     if (++bs == BST) { bs = 0; bph ^= 1; }
                     ts ^= 1; if (ts == 0) tph ^= 1;
+                    }
                     PROF_T(q3);
                     PROF_ADD(1, q2 - q0); PROF_ADD(2, q3 - q2); PROF_ADD(3, 1);   // [1] includes [0]
                 }
@@ -422,10 +448,11 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
         int staged_row0 = -1;
         uint32_t ts = 0, tph = 0;
         // bound mode: two warp groups, each owning one accumulator stage (see the tile loop)
-        constexpr int GNPART = NPART / 2;                 // column parts per tile inside a group
-        constexpr int GNCH = TILE_DB / CHUNK / (GNPART > 0 ? GNPART : 1);
-        const uint32_t grp = (uint32_t) part & 1u;        // accumulator stage / tile parity this warp serves
-        const int gpart = part >> 1;
+        // (four-stage variant: four groups, one per 128-column stage, every warp reduces a whole stage of its lane quadrant)
+        constexpr int GNPART = QUAD ? 1 : NPART / 2;      // column parts per stage inside a group
+        constexpr int GNCH = TS_COLS / CHUNK / (GNPART > 0 ? GNPART : 1);
+        const uint32_t grp = QUAD ? (uint32_t) part : ((uint32_t) part & 1u);        // accumulator stage this warp serves
+        const int gpart = QUAD ? 0 : (part >> 1);
         uint32_t gtile = 0, gph = 0;                      // running tile number at unit start, phase of the group's stage
         UnitCursor cur;
             for (int u = u_first; u < P.unit_end; u += u_step) {
@@ -457,16 +484,20 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                 // TMEM loads are software pipelined (chunk c+1 in flight while chunk c is reduced) and the stage
                 // is handed back to the MMA warp as soon as its last chunk sits in registers.
                 static_assert(BCHUNK % CHUNK == 0 && (GNCH * CHUNK) % BCHUNK == 0, "bound chunk must tile a column part");
-                const uint32_t tlane = tmem_base + ((uint32_t) (quad * 32) << 16) + grp * TILE_DB + gpart * (TILE_DB / GNPART);
-                for (int t = (int) ((grp ^ gtile) & 1u); t < U.ntiles_db; t += 2) {
-                    const int *nbs = sNall + t * TILE_DB + gpart * (TILE_DB / GNPART);
+                const uint32_t tlane = tmem_base + ((uint32_t) (quad * 32) << 16) + grp * TS_COLS + gpart * (TS_COLS / GNPART);
+                // hs = running stage-sized step inside the unit: a 256-column tile (two stages) or one of its 128-column halves (four)
+                constexpr int NSTEP = QUAD ? 2 : 1;       // steps per database tile
+                for (int hs = (int) ((grp - gtile) & (uint32_t) (NTS - 1)); hs < NSTEP * U.ntiles_db; hs += NTS) {
+                    const int t = QUAD ? (hs >> 1) : hs;
+                    const int gp = QUAD ? (hs & 1) : gpart;      // which 128-column half of tile t this warp reduces
+                    const int *nbs = sNall + t * TILE_DB + gp * 128;
                     PROF_T(e0);
                     mbar_wait(bar_t_full + 8 * grp, gph);
                     PROF_T(e1);
                     tc_fence_after();
                     uint32_t va[32], vb[32];
                     auto bookkeep = [&](int vmax, int cb) {
-                        const int chunk_id = t * (TILE_DB / BCHUNK) + gpart * (GNCH * CHUNK / BCHUNK) + cb;
+                        const int chunk_id = t * (TILE_DB / BCHUNK) + gp * (GNCH * CHUNK / BCHUNK) + cb;
                         const int lb = vmax * neg2 + nbs[cb * BCHUNK];
                         const int ub = vmax * neg2 + nbs[cb * BCHUNK + BCHUNK - 1];
                         const bool nb_best = lb < m1;
@@ -507,7 +538,7 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
                     if (warp == 2 && lane == 0) PROF_ADD(10, clock64() - e1);   // whole tile after the wait
 #endif
                 }
-                gtile += (uint32_t) U.ntiles_db;
+                gtile += (uint32_t) (NSTEP * U.ntiles_db);
             } else {
             int nrm_next = (!whole && etid < TILE_DB) ? P.norms[(size_t) U.db_row0 + etid] : 0;
             for (int t = 0; t < U.ntiles_db; t++) {
@@ -638,6 +669,7 @@ __device__ __forceinline__ void match_tc_body(const MatchParams &P)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(MatchParams P) { match_tc_body<false, false>(P); }
 __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_bound_kernel(MatchParams P) { match_tc_body<true, false>(P); }
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_quad_kernel(MatchParams P) { match_tc_body<true, false, true>(P); }
 // launched with cluster dimension (2, 1, 1)
 __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_pair_kernel(MatchParams P) { match_tc_body<true, true>(P); }
 

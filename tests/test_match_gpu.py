@@ -11,11 +11,13 @@ from bundler_sfm_b200 import keymatch, synth
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "match_golden.npz")
 # every kernel variant of the library runs the whole suite:
-#   tc       tcgen05 kernel, bound epilogue, one CTA per unit (the default)
+#   tc       tcgen05 kernel, bound epilogue, one CTA per unit, two accumulator stages of 256 columns
+#   tc_quad  the same with four accumulator stages of 128 columns
 #   tc_exact tcgen05 kernel, exact chunk-minimum epilogue (also the path of images > 8192 rows)
 #   tc_pair  tcgen05 cta_group::2 kernel on CTA pairs
 #   dp4a     CUDA-core kernel
-KERNELS = {"tc": {"BSFM_MATCH_KERNEL": "0"},
+KERNELS = {"tc": {"BSFM_MATCH_KERNEL": "0", "BSFM_MATCH_QUAD": "0"},
+           "tc_quad": {"BSFM_MATCH_KERNEL": "0", "BSFM_MATCH_QUAD": "1"},
            "tc_exact": {"BSFM_MATCH_KERNEL": "0", "BSFM_MATCH_EPILOGUE": "0"},
            "tc_pair": {"BSFM_MATCH_KERNEL": "0", "BSFM_MATCH_PAIR": "1"},
            "dp4a": {"BSFM_MATCH_KERNEL": "1"}}
@@ -23,7 +25,7 @@ KERNELS = {"tc": {"BSFM_MATCH_KERNEL": "0"},
 
 @pytest.fixture(params=list(KERNELS))
 def kernel(request, monkeypatch):
-    for k in ("BSFM_MATCH_KERNEL", "BSFM_MATCH_EPILOGUE", "BSFM_MATCH_PAIR"):
+    for k in ("BSFM_MATCH_KERNEL", "BSFM_MATCH_EPILOGUE", "BSFM_MATCH_PAIR", "BSFM_MATCH_QUAD"):
         monkeypatch.delenv(k, raising=False)
     for k, v in KERNELS[request.param].items():
         monkeypatch.setenv(k, v)

@@ -22,3 +22,15 @@ extern "C" int ref_keys_match(int n1, unsigned char *k1, int n2, unsigned char *
     for (int i = 0; i < cnt && i < cap; i++) { out_pairs[2 * i] = m[i].m_idx1; out_pairs[2 * i + 1] = m[i].m_idx2; }
     return cnt;
 }
+
+/* the in-bundler key reader (src/keys.cpp:155-200: text, .gz, .bin, .bin.gz): descriptors and (x, y) of every key */
+extern "C" int ref_read_key_file_with_desc(const char *filename, unsigned char *desc_out, float *xy_out, int cap)
+{
+    std::vector<KeypointWithDesc> k = ReadKeyFileWithDesc(filename, true);
+    int n = (int) k.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        for (int j = 0; j < 128; j++) desc_out[(size_t) 128 * i + j] = k[i].m_d[j];
+        xy_out[2 * i] = k[i].m_x; xy_out[2 * i + 1] = k[i].m_y;
+    }
+    return n;
+}

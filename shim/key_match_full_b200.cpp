@@ -95,7 +95,18 @@ int main(int argc, char **argv)
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < nthreads; t++)
             pool.emplace_back([&, t]() {
-                for (int i = (int) t; i < num_images; i += (int) nthreads) num_keys[i] = bsfm_shim_read_key_file(key_files[i].c_str(), &keys[i]);
+                // BSFM_WRITE_KEY_BIN=1: leave a binary cache <name>.bin (the layout src/keys.cpp:551-648 reads) beside every text file
+                const bool write_bin = getenv("BSFM_WRITE_KEY_BIN") != NULL;
+                for (int i = (int) t; i < num_images; i += (int) nthreads) {
+                    if (!write_bin) { num_keys[i] = bsfm_shim_read_key_file(key_files[i].c_str(), &keys[i]); continue; }
+                    float *info = NULL;
+                    num_keys[i] = bsfm_shim_read_key_file_info(key_files[i].c_str(), &keys[i], &info);
+                    if (num_keys[i] > 0 && info) {
+                        FILE *probe = fopen(key_files[i].c_str(), "r");      // only when the TEXT file itself was the source
+                        if (probe) { fclose(probe); bsfm_shim_write_key_bin((key_files[i] + ".bin").c_str(), num_keys[i], keys[i], info); }
+                    }
+                    delete[] info;
+                }
             });
         for (auto &th : pool) th.join();
     }

@@ -13,8 +13,18 @@
  * this reader slurps the file and converts digits by hand, and is safe to call from several threads.            */
 #ifndef BSFM_KEYFILE_B200_H
 #define BSFM_KEYFILE_B200_H
+/* Binary key cache (row (f)2 of SURVEY.md section 8): when neither <filename> nor <filename>.gz exists the reader accepts
+ * <filename>.bin / <filename>.bin.gz in the layout of the in-bundler readers ReadKeysFastBin / ReadKeysFastBinGzip
+ * (src/keys.cpp:551-648): int32 num | num x keypt_t {x, y, scale, orient} | num x 128 bytes; bsfm_shim_write_key_bin writes it
+ * (KeyMatchFull_b200_persistent does so for every text file it parsed when BSFM_WRITE_KEY_BIN=1: the next run, and
+ * `bundler`, skip the text parse).  `info` (nullable) receives the keypt_t array (new float[4 * num], caller delete[]s). */
 #ifdef __cplusplus
-extern "C"
+extern "C" {
 #endif
 int bsfm_shim_read_key_file(const char *filename, unsigned char **keys);
+int bsfm_shim_read_key_file_info(const char *filename, unsigned char **keys, float **info);
+int bsfm_shim_write_key_bin(const char *filename, int num, const unsigned char *keys, const float *info);
+#ifdef __cplusplus
+}
+#endif
 #endif

@@ -279,3 +279,36 @@ def test_match_pair_test_modes_vs_port(oracle):
             want = oracle.match_pair_port_test(imgs[0], imgs[1], ratio, mode)
             assert n == want.shape[0] and np.array_equal(out[:n], want), (mode, ratio)
     assert fn(imgs[0].ctypes.data, 900, imgs[1].ctypes.data, 1100, 0.6, 7, None, 0) < 0     # unknown test
+
+
+def test_binary_key_cache_roundtrip_and_reference_reader(tmp_path):
+    """<name>.bin in the layout of src/keys.cpp:551-648: written from a parsed text file, read back when the text file is gone,
+    and accepted by the UNMODIFIED in-bundler reader ReadKeyFileWithDesc (oracle/_ref/libref_keys.so)"""
+    if not os.path.exists(KEYFILE):
+        pytest.skip("shim/_build not built")
+    lib = ctypes.CDLL(KEYFILE)
+    rd = lib.bsfm_shim_read_key_file_info
+    rd.restype = ctypes.c_int
+    d = synth.sift_like_descriptors(1, [333], seed=9)[0]
+    txt = str(tmp_path / "a.key")
+    synth.write_key_file(txt, d, seed=3)
+    kbuf, ibuf = ctypes.POINTER(ctypes.c_ubyte)(), ctypes.POINTER(ctypes.c_float)()
+    n = rd(txt.encode(), ctypes.byref(kbuf), ctypes.byref(ibuf))
+    assert n == 333
+    keys = np.ctypeslib.as_array(kbuf, shape=(n * 128,)).reshape(n, 128).copy()
+    info = np.ctypeslib.as_array(ibuf, shape=(n * 4,)).reshape(n, 4).copy()
+    assert np.array_equal(keys, d)
+    assert lib.bsfm_shim_write_key_bin((txt + ".bin").encode(), n, keys.ctypes.data_as(ctypes.c_void_p), info.ctypes.data_as(ctypes.c_void_p)) == 1
+    os.remove(txt)                                   # only the cache is left: the reader falls through to <name>.bin
+    kbuf2, ibuf2 = ctypes.POINTER(ctypes.c_ubyte)(), ctypes.POINTER(ctypes.c_float)()
+    assert rd(txt.encode(), ctypes.byref(kbuf2), ctypes.byref(ibuf2)) == n
+    assert np.array_equal(np.ctypeslib.as_array(kbuf2, shape=(n * 128,)).reshape(n, 128), d)
+    assert np.array_equal(np.ctypeslib.as_array(ibuf2, shape=(n * 4,)).reshape(n, 4), info)
+    refso = os.path.join(ROOT, "oracle", "_ref", "libref_keys.so")
+    if os.path.exists(refso):                        # the reference's own reader on the file we wrote
+        ref = ctypes.CDLL(refso)
+        fn = ref.ref_read_key_file_with_desc
+        fn.restype = ctypes.c_int
+        out = np.zeros((n, 128), np.uint8); xy = np.zeros((n, 2), np.float32)
+        assert fn(txt.encode(), out.ctypes.data_as(ctypes.c_void_p), xy.ctypes.data_as(ctypes.c_void_p), n) == n
+        assert np.array_equal(out, d) and np.array_equal(xy, info[:, :2])

@@ -172,3 +172,14 @@ def test_config4_table_sampled_pairs_vs_oracle_and_reference_exact(oracle):
             assert np.array_equal(got, oracle.match_pair_ref(imgs[j], imgs[i], 0.6, 0)), ("reference exact mode", j, i)
             nref += 1
     assert not have_ref or nref >= 3
+
+
+def test_kermit_real_sift_table_equals_reference(kernel):
+    """BASELINE.json configs[0]'s MATCH stage on REAL descriptors: OpenCV-SIFT keys of the 11 kermit images, all 55 pairs, against
+    the stored exact-mode table of the unmodified reference (tests/golden/kermit_match_golden.npz, made by
+    make_kermit_match_golden.py); real data has near-duplicate keys and clipped descriptors that the synthetic sets lack"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kermit_match_golden.npz"))
+    descs = [g[f"desc{i}"] for i in range(int(g["num_images"]))]
+    pairs, counts, matches = keymatch.key_match_full(descs, -1, 0.6)
+    assert np.array_equal(counts, g["counts"]) and np.array_equal(matches, g["matches"])
+    assert (counts >= 16).sum() == 30

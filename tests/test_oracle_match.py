@@ -106,3 +106,20 @@ def test_port_keys_cpp_test_mode_vs_reference_exhaustive():
         assert want.shape[0] > 0
     # (a database of ONE key is a fatal error in the reference: ANN aborts with "Requesting more near neighbors than data
     #  points", lib/ann_1.1_char/src/kd_search.cpp -- not a case to compare)
+
+
+def test_port_on_real_sift_descriptors_kermit_golden():
+    """real SIFT descriptors of the reference's example set (examples/kermit, 11 images, 55 pairs): the C restatement against
+    the stored exact-mode output of the unmodified reference (tests/golden/kermit_match_golden.npz)"""
+    from oracle import loader
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kermit_match_golden.npz"))
+    n = int(g["num_images"])
+    descs = [g[f"desc{i}"] for i in range(n)]
+    pos, q = 0, 0
+    for i in range(n):
+        for j in range(i):
+            c = int(g["counts"][q])
+            assert np.array_equal(loader.match_pair_port(descs[j], descs[i], 0.6), g["matches"][pos:pos + c]), (j, i)
+            pos += c; q += 1
+    for (a, b) in ((0, 1), (3, 7), (10, 9)):
+        assert np.array_equal(loader.match_pair_port_test(descs[a], descs[b], 0.75, 1), g[f"keys_{a}_{b}"])

@@ -266,6 +266,20 @@ def test_keys_cpp_matchkeys_overload_equals_reference_exhaustive(oracle):
 
 
 @pytest.mark.gpu
+def test_keys_cpp_test_on_real_sift_kermit_golden():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kermit_match_golden.npz"))
+    lib = bundle.load_library()
+    fn = lib.bsfm_match_pair_test
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    fn.restype = ctypes.c_int
+    for (a, b) in ((0, 1), (3, 7), (10, 9)):
+        k1, k2 = np.ascontiguousarray(g[f"desc{a}"]), np.ascontiguousarray(g[f"desc{b}"])
+        out = np.zeros((k1.shape[0], 2), np.int32)
+        n = fn(k1.ctypes.data, k1.shape[0], k2.ctypes.data, k2.shape[0], 0.75, 1, out.ctypes.data, k1.shape[0])
+        assert np.array_equal(out[:n], g[f"keys_{a}_{b}"]), (a, b)
+
+
+@pytest.mark.gpu
 def test_match_pair_test_modes_vs_port(oracle):
     lib = bundle.load_library()
     fn = lib.bsfm_match_pair_test

@@ -20,16 +20,6 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def test_shard_range_equals_python_rule():
-    sizes = [5000] * 37 + [0, 17, 4000]
-    key_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    for world in (1, 2, 3, 8):
-        for window in (-1, 4):
-            want = keymatch.shard_images(sizes, window, world)
-            got = [keymatch.shard_range(key_off, window, world, r) for r in range(world)]
-            assert got == want, (world, window)
-
-
 def test_sharded_layout_single_rank():
     """a world-size-1 communicator exercises the cooperative build path (NCCL init, chunked layout) on one GPU"""
     sizes = [700, 0, 300, 17, 513, 256, 1, 640]

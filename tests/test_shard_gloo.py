@@ -65,3 +65,13 @@ def test_gather_match_table_world2_gloo(tmp_path, window):
         assert np.array_equal(got["counts"], c_all)
         assert np.array_equal(got["matches"], m_all)
     assert c_all.sum() > 0
+
+
+def test_shard_range_equals_python_rule():
+    sizes = [5000] * 37 + [0, 17, 4000]
+    key_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        for window in (-1, 4):
+            want = keymatch.shard_images(sizes, window, world)
+            got = [keymatch.shard_range(key_off, window, world, r) for r in range(world)]
+            assert got == want, (world, window)

@@ -23,6 +23,8 @@
 namespace bsfm {
 namespace ba {
 
+int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *x, Scalars *sc, bool *used);
+
 constexpr int NB = 32;
 #ifdef BSFM_DEBUG_CLOCKS
 __device__ long long g_dbg[64];
@@ -466,6 +468,11 @@ int chol_solve(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws,
     // BSFM_BA_CHOL_LARGE_MIN moves the switch-over (tests run the large path on small systems with it)
     static const int large_min = []() { const char *e = getenv("BSFM_BA_CHOL_LARGE_MIN"); return e ? atoi(e) : 1536; }();
     static const bool old_large = getenv("BSFM_BA_CHOL_OLD") != nullptr;      // round-1 large path (32-column steps + DMMA), kept for A/B timing
+    if (n <= large_min && n > LNB) {      // small systems: one co-resident dataflow launch per factorisation (ba_chol_dataflow.cu)
+        bool used = false;
+        int rc = chol_solve_dataflow(st, A, Lmat, n, linv_ws, x, sc, &used);
+        if (rc != BSFM_OK || used) return rc;
+    }
     if (n > large_min && !old_large) return chol_solve_large(st, A, Lmat, n, linv_ws, linv_ws + (size_t) ((n + NB - 1) / NB) * NB * NB, x, sc, ws);
     const int ld = n, nrows = n + 1;
     const int nbk = (n + NB - 1) / NB;

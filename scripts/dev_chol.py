@@ -62,6 +62,12 @@ def main():
                           f"epilogue/level wait {v[8]/lv:.0f} fold {v[9]/lv:.0f} | write-back/tile {v[10]/tl:.0f}  ({v[3]} levels, {v[11]} tiles)", flush=True)
             print(f"    per solve: diag {pms[0]/3:.3f} ms ({pl[0]//3} launches)  trsm {pms[1]/3:.3f} ms  trailing {pms[2]/3:.3f} ms "
                   f"({fl.value/3/(pms[2]/3*1e-3)/1e12:.1f} TF/s fp64-equiv, {ops.value/3/(pms[2]/3*1e-3)/1e12:.0f} TOP/s int8)  backsolve {pms[3]/3:.3f} ms", flush=True)
+        if os.environ.get("BSFM_DF_PROF") and hasattr(lib, "bsfm_debug_df_prof"):
+            dp = (ctypes.c_uint64 * 8)()
+            if lib.bsfm_debug_df_prof(dp) == 0 and dp[7]:
+                v = list(dp); st = max(v[6], 1)
+                print(f"    dataflow CTA0: kernel {v[0]/v[7]/1e3:.1f} us/launch; cycles/step: potf2 {v[1]/st:.0f}  wait-loads {v[2]/st:.0f}  solve {v[3]/st:.0f}  "
+                      f"wait-publish {v[4]/st:.0f}  phase3 {v[5]/st:.0f}  ({v[6]} steps, {v[7]} launches)", flush=True)
         if rc != 1:
             print(f"[{tag}] n={n}: rc={rc} err={lib.bsfm_last_error()}")
             continue

@@ -26,7 +26,6 @@ namespace bsfm {
 namespace ba {
 
 constexpr int DF_THREADS = 256;
-constexpr int DF_LD = LNB + 1;
 constexpr long long DF_SPIN_LIMIT = 400000;      // polls of ~0.5-1 us: a lost flag costs well under a second, never a hang
 
 __device__ __forceinline__ int ld_acquire(const int *p)
@@ -52,24 +51,6 @@ __device__ __forceinline__ void df_wait(const int *flag, int need, Scalars *sc)
     __syncthreads();
 }
 
-// x <- x L^-T for one 32-wide row per thread (row in registers), L lower triangular in shared memory, dinv = 1 / diag
-__device__ __forceinline__ void row_solve_32(double *xrow /* DF_LD pitch row in smem */, const double (*Ls)[DF_LD], const double *dinv)
-{
-    double v[LNB];
-#pragma unroll
-    for (int c = 0; c < LNB; c++) v[c] = xrow[c];
-#pragma unroll
-    for (int t = 0; t < LNB; t++) {
-        const double x = v[t] * dinv[t];
-        v[t] = x;
-#pragma unroll
-        for (int c = 1; c < LNB; c++)
-            if (c > t) v[c] = fma(-x, Ls[c][t], v[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < LNB; c++) xrow[c] = v[c];
-}
-
 // tile index of (rb, cb), 1 <= cb <= rb <= nbk (block row nbk = right-hand side), column-major over cb
 __device__ __forceinline__ int df_tile_index(int rb, int cb, int nbk)
 {
@@ -85,36 +66,26 @@ __device__ __forceinline__ unsigned long long df_clock() { unsigned long long t;
 __device__ __forceinline__ unsigned long long df_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
 
 __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A, double *Lout, int ld, int n, double *linv_all, Scalars *sc,
-                                                                     int *ver /* (nbk+1) x (nbk+1) tile versions, init -1 */, int *diag_ready /* nbk, init -1 */)
+                                                                     int *ver /* (nbk+1) x (nbk+1) tile versions, init -1 */, int *diag_ready /* nbk, init -1 */, int variant /* dev experiments */)
 {
-    __shared__ double Ls[LNB][DF_LD];        // L_kk
-    __shared__ double Xr[LNB][DF_LD];
-    __shared__ double Xc[LNB][DF_LD];
-    __shared__ double Zs[LNB][DF_LD];
+    __shared__ __align__(16) double tiles[5][LNB][TP];      // CTA 0: L_kk, next diagonal tile, X, Z, W;  workers: Z, X_r, X_c
     __shared__ double dinv[LNB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tg = lane & 3;
     const int nbk = (n + LNB - 1) / LNB;
     const int VW = nbk + 1;                  // row pitch of `ver`
     const int workers = (int) gridDim.x - 1;
 
     auto rows_of = [&](int rb) { return (rb == nbk) ? 1 : min(LNB, n - rb * LNB); };
     auto rbase_of = [&](int rb) { return (rb == nbk) ? n : rb * LNB; };
-    // load block (rb, cb) of A (rows x width, zero padded) into smem
-    auto load_block = [&](double (*dst)[DF_LD], int rb, int cb, int width) {
-        const int rows = rows_of(rb), rbase = rbase_of(rb), c0 = cb * LNB;
-        for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-            const int r = e >> 5, c = e & 31;
-            dst[r][c] = (r < rows && c < width) ? __ldcg(&A[(size_t) (rbase + r) * ld + (c0 + c)]) : 0.0;     // L2: written by another SM
-        }
-    };
 
     if (blockIdx.x == 0) {
         // ================= the diagonal chain =================
-        // warp 0 runs the chain (potf2 -> solve of the sub-diagonal block -> rank-32 update of the next diagonal tile, which never
-        // leaves shared memory); warps 1..7 hide everything else under it: they poll the flags and fetch the blocks of the NEXT
-        // look-ahead while warp 0 factors, and publish L_kk / form L_kk^-1 while warp 0 solves.
-        __shared__ double Dn[LNB][DF_LD];        // the next diagonal tile
-        double (*Lc)[DF_LD] = Ls, (*Ln)[DF_LD] = Dn;
+        // warp 0 factors the diagonal tile (warp_potf2_32_tc), warp 1 assembles its inverse one panel behind, warps 2..7 poll the
+        // flags and fetch the inputs of the look-ahead meanwhile.  Then: X <- X Z^T for the sub-diagonal block (warps 0..3, DMMA)
+        // while warps 4..7 publish L_kk and Z_kk; then the rank-32 update of the next diagonal tile, which never leaves shared memory.
+        double (*Lc)[TP] = tiles[0], (*Ln)[TP] = tiles[1];
+        double (*Xr)[TP] = tiles[2], (*Zs)[TP] = tiles[3], (*Ws)[TP] = tiles[4];
         const unsigned long long ns0 = df_ns();
         unsigned long long pc[5] = {0, 0, 0, 0, 0}, tc = 0;
         {
@@ -122,6 +93,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
             for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
                 const int r = e >> 5, c = e & 31;
                 Lc[r][c] = (r < nb0 && c <= r) ? A[(size_t) r * ld + c] : ((r == c) ? 1.0 : 0.0);
+                Zs[r][c] = 0.0;                              // the strictly upper blocks of Z stay zero
             }
         }
         __syncthreads();
@@ -130,24 +102,24 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
             const bool last = (k + 1 == nbk);
             const int rb = last ? nbk : k + 1;                 // last step: the right-hand side segment instead of a diagonal tile
             const int rrows = rows_of(rb), rbase = rbase_of(rb);
-            // ---- phase 1: potf2(k)  ||  inputs of the look-ahead ----
+            // ---- phase 1: potf2(k) and its inverse  ||  inputs of the look-ahead ----
             tc = df_clock();
             if (warp == 0) {
-                const bool bad = warp_potf2_32<DF_LD>(Lc, dinv, lane);
+                const bool bad = warp_potf2_32_tc(Lc, dinv, lane, true);
                 if (bad && lane == 0) sc->chol_fail = 1;
-                __syncwarp();
-                dinv[lane] = 1.0 / Lc[lane][lane];               // the divisors every CTA uses (the workers form them the same way)
                 { const unsigned long long t = df_clock(); pc[0] += t - tc; tc = t; }
+            } else if (warp == 1) {
+                warp_tile_inverse(Lc, dinv, Zs, Ws, lane);
             } else {
-                if (tid == 32) {
+                if (tid == 64) {
                     long long spins = 0;
                     while (ld_acquire(&ver[rb * VW + k]) < k - 1 || (!last && ld_acquire(&ver[rb * VW + rb]) < k - 1)) {
                         if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
                         __nanosleep(20);
                     }
                 }
-                asm volatile("bar.sync 1, 224;" ::: "memory");
-                for (int e = tid - 32; e < LNB * LNB; e += DF_THREADS - 32) {
+                asm volatile("bar.sync 1, 192;" ::: "memory");
+                for (int e = tid - 64; e < LNB * LNB; e += DF_THREADS - 64) {
                     const int r = e >> 5, c = e & 31;
                     Xr[r][c] = (r < rrows && c < nb) ? __ldcg(&A[(size_t) (rbase + r) * ld + (k0 + c)]) : 0.0;
                     if (!last) Ln[r][c] = (r < rrows && c <= r) ? __ldcg(&A[(size_t) (rbase + r) * ld + (rbase + c)]) : ((r == c) ? 1.0 : 0.0);
@@ -155,51 +127,46 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
             }
             __syncthreads();
             { const unsigned long long t = df_clock(); pc[1] += t - tc; tc = t; }
-            // ---- phase 2: solve of the sub-diagonal block  ||  publish L_kk, form L_kk^-1 ----
-            if (warp == 0) {
-                if (lane < rrows) row_solve_32(Xr[lane], Lc, dinv);
+            // ---- phase 2: sub-diagonal block X <- X Z^T  ||  publish L_kk and Z_kk ----
+            const int role = (variant & 4) ? (warp ^ 4) : warp;          // dev: swap which half solves and which half publishes
+            if (role < 4) {
+                warp_rows_times_ZT(Xr, 8 * role, Zs, lane);
                 { const unsigned long long t = df_clock(); pc[2] += t - tc; tc = t; }
             } else {
-                for (int e = tid - 32; e < LNB * LNB; e += DF_THREADS - 32) {
+                for (int e = (tid ^ ((variant & 4) ? 128 : 0)) - 128; e < LNB * LNB; e += 128) {
                     const int r = e >> 5, c = e & 31;
                     if (r < nb && c <= r) Lout[(size_t) (k0 + r) * ld + (k0 + c)] = Lc[r][c];
+                    linv_all[(size_t) k * LNB * LNB + e] = (c <= r) ? Zs[r][c] : 0.0;
                 }
-                __threadfence();
-                asm volatile("bar.sync 1, 224;" ::: "memory");
-                if (tid == 32) st_release(&diag_ready[k], 1);
-                if (warp == DF_THREADS / 32 - 1) {
-                    double v[LNB];
-#pragma unroll
-                    for (int r = 0; r < LNB; r++) v[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int t = 0; t < LNB; t++) {
-                        const double z = v[t] * dinv[t];
-                        v[t] = z;
-#pragma unroll
-                        for (int r = 1; r < LNB; r++)
-                            if (r > t) v[r] = fma(-Lc[r][t], z, v[r]);
-                    }
-#pragma unroll
-                    for (int r = 0; r < LNB; r++) Zs[r][lane] = v[r];
+                asm volatile("bar.sync 6, 128;" ::: "memory");
+                if (tid == ((variant & 4) ? 0 : ((variant & 1) ? 224 : 128))) {      // one cumulative fence after the barrier, not 128
+                    if (variant & 2) *reinterpret_cast<volatile int *>(&diag_ready[k]) = 1;        // dev: timing without the fence (NOT correct)
+                    else { __threadfence(); st_release(&diag_ready[k], 1); }
                 }
             }
             __syncthreads();
             { const unsigned long long t = df_clock(); pc[3] += t - tc; tc = t; }
-            // ---- phase 3: factor block, inverse, rank-32 update of the next diagonal tile (stays in shared memory) ----
+            // ---- phase 3: factor block out, rank-32 update of the next diagonal tile (stays in shared memory) ----
             for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
                 const int r = e >> 5, c = e & 31;
                 if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
-                linv_all[(size_t) k * LNB * LNB + e] = (c <= r) ? Zs[r][c] : 0.0;
-                if (!last && r < rrows && c <= r) {
-                    double acc = 0.0;
-#pragma unroll 8
-                    for (int t = 0; t < LNB; t++) acc = fma(Xr[r][t], Xr[c][t], acc);
-                    Ln[r][c] -= acc;
+            }
+            if (!last) {
+                for (int t = warp; t < 10; t += DF_THREADS / 32) {       // lower 8 x 8 tiles (ri, cj)
+                    int ri = 0, rem = t;
+                    while (rem > ri) { rem -= ri + 1; ri++; }
+                    const int cj = rem;
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < LNB; ks += 4) tile_dmma(c0, c1, Xr[8 * ri + g][ks + tg], Xr[8 * cj + g][ks + tg]);
+                    double2 cur = *reinterpret_cast<const double2 *>(&Ln[8 * ri + g][8 * cj + 2 * tg]);
+                    cur.x -= c0; cur.y -= c1;
+                    *reinterpret_cast<double2 *>(&Ln[8 * ri + g][8 * cj + 2 * tg]) = cur;
                 }
             }
             __syncthreads();
             { const unsigned long long t = df_clock(); pc[4] += t - tc; tc = t; }
-            double (*tmp)[DF_LD] = Lc; Lc = Ln; Ln = tmp;
+            double (*tmp)[TP] = Lc; Lc = Ln; Ln = tmp;
         }
         if (tid == 0) {
             g_df_prof[0] += df_ns() - ns0;
@@ -211,24 +178,28 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
     }
 
     // ================= workers: static tile ownership =================
+    double (*Zs)[TP] = tiles[0], (*Xr)[TP] = tiles[1], (*Xc)[TP] = tiles[2];
+    // load block (rb, cb) of A (rows x width, zero padded) into smem
+    auto load_block = [&](double (*dst)[TP], int rb, int cb, int width) {
+        const int rows = rows_of(rb), rbase = rbase_of(rb), c0 = cb * LNB;
+        for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
+            const int r = e >> 5, c = e & 31;
+            dst[r][c] = (r < rows && c < width) ? __ldcg(&A[(size_t) (rbase + r) * ld + (c0 + c)]) : 0.0;     // L2: written by another SM
+        }
+    };
     const int w = (int) blockIdx.x - 1;
     for (int k = 0; k + 1 <= nbk; k++) {
         const int k0 = k * LNB, nb = min(LNB, n - k0);
-        bool have_l = false;
+        bool have_z = false;
         // tiles (rb, cb), k < cb <= rb <= nbk, cb < nbk, owned by this CTA; (k+1, k+1) belongs to CTA 0 at this step
         for (int cb = k + 1; cb < nbk; cb++) {
             for (int rb = cb; rb <= nbk; rb++) {
                 if (df_tile_index(rb, cb, nbk) % workers != w) continue;
                 if (rb == cb && cb == k + 1) continue;
-                if (!have_l) {
+                if (!have_z) {
                     df_wait(&diag_ready[k], 1, sc);
-                    for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-                        const int r = e >> 5, c = e & 31;
-                        Ls[r][c] = (r < nb && c <= r) ? __ldcg(&Lout[(size_t) (k0 + r) * ld + (k0 + c)]) : ((r == c) ? 1.0 : 0.0);
-                    }
-                    __syncthreads();
-                    if (tid < LNB) dinv[tid] = 1.0 / Ls[tid][tid];
-                    have_l = true;
+                    for (int e = tid; e < LNB * LNB; e += DF_THREADS) Zs[e >> 5][e & 31] = __ldcg(&linv_all[(size_t) k * LNB * LNB + e]);
+                    have_z = true;
                 }
                 df_wait(&ver[rb * VW + k], k - 1, sc);
                 if (cb != rb) df_wait(&ver[cb * VW + k], k - 1, sc);
@@ -237,10 +208,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
                 if (cb != rb) load_block(Xc, cb, k, nb);
                 __syncthreads();
                 const int rrows = rows_of(rb), crows = rows_of(cb);
-                if (tid < rrows) row_solve_32(Xr[tid], Ls, dinv);
-                else if (cb != rb && tid >= 32 && tid < 32 + crows) row_solve_32(Xc[tid - 32], Ls, dinv);
+                // both panel blocks: X <- X Z^T, one 8-row strip per warp
+                if (warp < 4) warp_rows_times_ZT(Xr, 8 * warp, Zs, lane);
+                else if (cb != rb) warp_rows_times_ZT(Xc, 8 * (warp - 4), Zs, lane);
                 __syncthreads();
-                const double (*XC)[DF_LD] = (cb != rb) ? Xc : Xr;
+                const double (*XC)[TP] = (cb != rb) ? Xc : Xr;
                 const int rbase = rbase_of(rb), c0 = cb * LNB;
                 if (cb == k + 1) {          // first column: this tile's row block of the factor
                     for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
@@ -248,19 +220,22 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
                         if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
                     }
                 }
-                for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-                    const int r = e >> 5, c = e & 31;
-                    if (r < rrows && c < crows && (rb != cb || c <= r)) {
-                        double acc = 0.0;
-#pragma unroll 8
-                        for (int t = 0; t < LNB; t++) acc = fma(Xr[r][t], XC[c][t], acc);
-                        double *dst = &A[(size_t) (rbase + r) * ld + (c0 + c)];
-                        *dst = __ldcg(dst) - acc;
-                    }
+                // tile -= X_r X_c^T : sixteen 8 x 8 DMMA tiles, two per warp
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int t = warp * 2 + i, ri = t >> 2, cj = t & 3;
+                    if (rb == cb && cj > ri) continue;
+                    if (8 * ri >= rrows || 8 * cj >= crows) continue;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < LNB; ks += 4) tile_dmma(a0, a1, Xr[8 * ri + g][ks + tg], XC[8 * cj + g][ks + tg]);
+                    const int r = 8 * ri + g, c = 8 * cj + 2 * tg;
+                    double *dst = &A[(size_t) (rbase + r) * ld + (c0 + c)];
+                    if (r < rrows && c < crows && (rb != cb || c <= r)) dst[0] = __ldcg(dst) - a0;
+                    if (r < rrows && c + 1 < crows && (rb != cb || c + 1 <= r)) dst[1] = __ldcg(dst + 1) - a1;
                 }
-                __threadfence();
                 __syncthreads();
-                if (tid == 0) st_release(&ver[rb * VW + cb], k);
+                if (tid == 0) { __threadfence(); st_release(&ver[rb * VW + cb], k); }
             }
         }
     }
@@ -297,7 +272,8 @@ int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double 
     if (nbk < 2 || nbk > df_max_blocks()) return BSFM_OK;      // larger systems: the workers' serial tile loop loses to the fused-step path
     int ntile = 0;
     for (int c = 1; c < nbk; c++) ntile += nbk - c + 1;
-    const int grid = std::min(sm_count[dev].load(), 1 + std::max(1, ntile));
+    static const int grid_cap = []() { const char *e = getenv("BSFM_DF_GRID"); return e ? atoi(e) : 1 << 20; }();      // dev experiments
+    const int grid = std::min(grid_cap, std::min(sm_count[dev].load(), 1 + std::max(1, ntile)));
     if (grid < 2) return BSFM_OK;
     // flags live behind the back-substitution scratch of the workspace (chol_extra_ws_doubles leaves > 64k doubles there)
     double *ywork = linv_ws + (size_t) nbk * LNB * LNB;
@@ -305,7 +281,9 @@ int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double 
     int *ver = flags, *diag_ready = flags + (nbk + 1) * (nbk + 1);
     BSFM_CUDA_TRY(cudaMemsetAsync(flags, 0xFF, (size_t) ((nbk + 1) * (nbk + 1) + nbk + 8) * sizeof(int), st));
     int ld = n;
-    void *args[] = {&A, &Lmat, &ld, &n, &linv_ws, &sc, &ver, &diag_ready};
+    static const int variant = []() { const char *e = getenv("BSFM_DF_VARIANT"); return e ? atoi(e) : 0; }();
+    int var = variant;
+    void *args[] = {&A, &Lmat, &ld, &n, &linv_ws, &sc, &ver, &diag_ready, &var};
     BSFM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *) chol_dataflow_kernel, dim3(grid), dim3(DF_THREADS), args, 0, st));
     count_launch();
     chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, ld, n, linv_ws, x, ywork);

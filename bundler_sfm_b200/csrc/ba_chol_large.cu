@@ -16,6 +16,7 @@
 // throughput-bound.
 #include "ba_kernels.cuh"
 #include "ba_chol_large.cuh"
+#include "ba_chol_potf2.cuh"
 #include "common.h"
 #include <algorithm>
 #include <atomic>
@@ -46,21 +47,24 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 // Shared-memory row pitch 36 doubles: conflict-free for the DMMA fragment pattern [row g][column tg].
 constexpr int DG_LD = LNB + 4;
 constexpr int DG_XROWS = LNBO - LNB;          // 224 panel rows at most inside the diagonal block
-constexpr int DG_SMEM_DOUBLES = (2 * LNB + DG_XROWS) * DG_LD + LNB;
+constexpr int DG_SMEM_DOUBLES = (3 * LNB + DG_XROWS) * DG_LD + LNB;
+static_assert(DG_LD == TP, "tile primitives of ba_chol_potf2.cuh use a pitch of 36 doubles");
 constexpr int DG_THREADS = 256;    // 255 registers per thread: the register-resident 32-wide rows need them
 __global__ void __launch_bounds__(DG_THREADS, 1) chol_diag_kernel(double *A, double *Lout, int ld, int n, int k0, double *linv_all, Scalars *sc, long long *dbg)
 {
 #define DG_T(i) do { if (dbg && tid == 0) { const long long now = clock64(); dbg[i] += now - tlast; tlast = now; } } while (0)
     long long tlast = dbg ? clock64() : 0;
-    extern __shared__ double dsm[];
+    extern __shared__ __align__(16) double dsm[];
     double (*Ls)[DG_LD] = reinterpret_cast<double (*)[DG_LD]>(dsm);
     double (*Zs)[DG_LD] = reinterpret_cast<double (*)[DG_LD]>(dsm + LNB * DG_LD);
-    double (*Xs)[DG_LD] = reinterpret_cast<double (*)[DG_LD]>(dsm + 2 * LNB * DG_LD);
-    double *dinv = dsm + (2 * LNB + DG_XROWS) * DG_LD;
+    double (*Ws)[DG_LD] = reinterpret_cast<double (*)[DG_LD]>(dsm + 2 * LNB * DG_LD);
+    double (*Xs)[DG_LD] = reinterpret_cast<double (*)[DG_LD]>(dsm + 3 * LNB * DG_LD);
+    double *dinv = dsm + (3 * LNB + DG_XROWS) * DG_LD;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tg = lane & 3;
     const int nb = min(LNBO, n - k0);
     const int nsub = (nb + LNB - 1) / LNB;
+    for (int e = tid; e < LNB * DG_LD; e += DG_THREADS) Zs[0][e] = 0.0;       // the strictly upper blocks of Z stay zero
     for (int s = 0; s < nsub; s++) {
         const int c0 = k0 + s * LNB;                      // first matrix column of the sub-block
         const int w = min(LNB, k0 + nb - c0);             // its width
@@ -86,76 +90,19 @@ __global__ void __launch_bounds__(DG_THREADS, 1) chol_diag_kernel(double *A, dou
         __syncthreads();
         DG_T(0);
         if (warp == 0) {
-            // potf2 of the 32 x 32 block: lane = row.  Four 8-column panels: the panel lives in registers (8 pivots
-            // unrolled, multipliers by shuffle), the columns right of it are updated in shared memory in a run-time
-            // loop.  (A fully unrolled 32-pivot register version is ~3000 straight-line instructions and ran at the
-            // instruction-fetch rate: 1060 cycles per pivot.)
-            bool bad = false;
-            for (int jb = 0; jb < LNB; jb += 8) {
-                double p[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) p[q] = Ls[lane][jb + q];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int j = jb + q;
-                    const double d = shfl_d(p[q], j);
-                    const bool isbad = !(d > 0.0) || !isfinite(d);
-                    bad |= isbad;
-                    const double rinv = isbad ? 1.0 : rsqrt(d);
-                    const double l = p[q] * rinv;               // lane == j: sqrt(d); lane > j: L[lane][j]; lane < j: 0
-                    p[q] = l;
-                    if (lane == j) dinv[j] = rinv;
-#pragma unroll
-                    for (int q2 = 1; q2 < 8; q2++) {
-                        if (q2 > q) {
-                            const double lc = shfl_d(l, jb + q2);
-                            if (lane >= jb + q2) p[q2] = fma(-l, lc, p[q2]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) Ls[lane][jb + q] = (jb + q <= lane) ? p[q] : 0.0;
-#pragma unroll 2
-                for (int c = jb + 8; c < LNB; c++) {
-                    double v = Ls[lane][c];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) v = fma(-p[q], shfl_d(p[q], c), v);
-                    if (lane >= c) Ls[lane][c] = v;
-                }
-            }
+            // potf2 of the 32 x 32 block (ba_chol_potf2.cuh): lane = row, 8-column register panels, DMMA rank-8 updates
+            const bool bad = warp_potf2_32_tc(Ls, dinv, lane, true);
             if (bad && lane == 0) sc->chol_fail = 1;
+            DG_T(5);                                            // dev accounting: potf2 alone; slot 1 is then the wait for the inverse
+        } else if (warp == 1) {
+            const long long t1 = dbg ? clock64() : 0;
+            warp_tile_inverse(Ls, dinv, Zs, Ws, lane);          // Z = L_ss^-1 assembled one panel behind warp 0
+            if (dbg && lane == 0) dbg[6] += clock64() - t1;
         }
         __syncthreads();
         DG_T(1);
-        if (tid < below) {
-            double v[LNB];
-#pragma unroll
-            for (int c = 0; c < LNB; c++) v[c] = Xs[tid][c];
-#pragma unroll
-            for (int t = 0; t < LNB; t++) {
-                const double x = v[t] * dinv[t];
-                v[t] = x;
-#pragma unroll
-                for (int c = 1; c < LNB; c++)
-                    if (c > t) v[c] = fma(-x, Ls[c][t], v[c]);
-            }
-#pragma unroll
-            for (int c = 0; c < LNB; c++) Xs[tid][c] = v[c];
-        } else if (warp == DG_THREADS / 32 - 1) {
-            double v[LNB];
-#pragma unroll
-            for (int r = 0; r < LNB; r++) v[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int t = 0; t < LNB; t++) {
-                const double z = v[t] * dinv[t];
-                v[t] = z;
-#pragma unroll
-                for (int r = 1; r < LNB; r++)
-                    if (r > t) v[r] = fma(-Ls[r][t], z, v[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < LNB; r++) Zs[r][lane] = v[r];
-        }
+        // panel rows below the sub-block: X <- X L_ss^-T = X Z^T, 8-row strips on the fp64 tensor cores
+        for (int strip = warp; strip * 8 < below; strip += DG_THREADS / 32) warp_rows_times_ZT(Xs, strip * 8, Zs, lane);
         __syncthreads();
         DG_T(2);
         for (int e = tid; e < LNB * LNB; e += DG_THREADS) {

@@ -52,7 +52,7 @@ def main():
                 dp = (ctypes.c_int64 * 8)()
                 if lib.bsfm_debug_diag_prof(dp) == 0:
                     v = [x / 3 / 1.9e3 for x in dp]     # 3 solves since the reset, us at 1.9 GHz
-                    print(f"    diag panel 0 (us, approx): load {v[0]:.1f}  potf2 {v[1]:.1f}  rowsolve+inv {v[2]:.1f}  store {v[3]:.1f}  trailing {v[4]:.1f}", flush=True)
+                    print(f"    diag panel 0 (us, approx): load {v[0]:.1f}  potf2 {v[1]:.1f}  rowsolve+inv {v[2]:.1f}  store {v[3]:.1f}  trailing {v[4]:.1f} | potf2 alone {v[5]:.1f}  inverse warp (incl. waits) {v[6]:.1f}", flush=True)
             if os.environ.get("BSFM_TCS_PROF"):
                 pr = (ctypes.c_uint64 * 16)()
                 if lib.bsfm_debug_tcs_prof(pr) == 0:

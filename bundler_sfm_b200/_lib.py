@@ -78,6 +78,8 @@ def load_library():
     lib.bsfm_match_pair_cache_clear.restype = None
     lib.bsfm_measure_int8_peak.argtypes = [c.c_int, c.c_int]
     lib.bsfm_measure_int8_peak.restype = c.c_double
+    lib.bsfm_measure_fp64_issue_cycles.argtypes = [c.c_int, c.c_int, c.c_int]
+    lib.bsfm_measure_fp64_issue_cycles.restype = c.c_double
     _LIB = lib
     return lib
 

@@ -415,18 +415,23 @@ __global__ void __launch_bounds__(512) chol_backsolve_blocked_kernel(const doubl
     double y0 = (tid < n) ? yrow[tid] : 0.0;
     for (int c = tid + 512; c < n; c += 512) ywork[c] = yrow[c];
     const int nbk = (n + NB - 1) / NB;
-    for (int kb = nbk - 1; kb >= 0; kb--) {
-        const int k0 = kb * NB, nb = min(NB, n - k0);
-        // everything that does not depend on x_k is issued first: L_kk^-1 block and this thread's
-        // column of the 32 L rows (first 512 columns)
-        const double z0 = Linv_all[(size_t) kb * NB * NB + tid], z1 = Linv_all[(size_t) kb * NB * NB + 512 + tid];
-        double l[NB];
+    // Nothing loaded here depends on x: the inverse block of step kb - 1 is fetched one step ahead and this thread's column of
+    // the 32 factor rows of step kb - 1 is requested the moment the registers of step kb are dead, so the L2 latency of both
+    // hides under the shared-memory part of the step (the steps are otherwise a chain of ~1 us global loads).
+    double z0 = 0.0, z1 = 0.0, l[NB];
+    {
+        const int kb = nbk - 1, k0 = kb * NB, nb = min(NB, n - k0);
+        z0 = Linv_all[(size_t) kb * NB * NB + tid]; z1 = Linv_all[(size_t) kb * NB * NB + 512 + tid];
 #pragma unroll
         for (int r = 0; r < NB; r++) l[r] = (tid < k0 && r < nb) ? A[(size_t) (k0 + r) * ld + tid] : 0.0;
+    }
+    for (int kb = nbk - 1; kb >= 0; kb--) {
+        const int k0 = kb * NB, nb = min(NB, n - k0);
         if (tid >= k0 && tid < k0 + nb) ys[tid - k0] = y0;
         for (int c = tid + 512; c < k0 + nb; c += 512) if (c >= k0) ys[c - k0] = ywork[c];
         Li[tid >> 5][tid & 31] = z0;
         Li[16 + (tid >> 5)][tid & 31] = z1;
+        if (kb > 0) { z0 = Linv_all[(size_t) (kb - 1) * NB * NB + tid]; z1 = Linv_all[(size_t) (kb - 1) * NB * NB + 512 + tid]; }
         __syncthreads();
         // x_k = L_kk^-T y_k : 8 lanes per output, 4 terms each, shuffle-reduced
         if (tid < 256) {
@@ -446,16 +451,25 @@ __global__ void __launch_bounds__(512) chol_backsolve_blocked_kernel(const doubl
             for (int r = 0; r < NB; r++) sacc = fma(l[r], xk[r], sacc);
             y0 -= sacc;
         }
-        for (int c = tid + 512; c < k0; c += 512) {
-            double lv[NB];
-#pragma unroll
-            for (int r = 0; r < NB; r++) lv[r] = (r < nb) ? A[(size_t) (k0 + r) * ld + c] : 0.0;
+        for (int c = tid + 512; c < k0; c += 512) {      // systems beyond 512 columns: 16 rows at a time (register budget)
             double sacc = 0.0;
+#pragma unroll 1
+            for (int r0 = 0; r0 < NB; r0 += 16) {
+                double lv[16];
 #pragma unroll
-            for (int r = 0; r < NB; r++) sacc = fma(lv[r], xk[r], sacc);
+                for (int r = 0; r < 16; r++) lv[r] = (r0 + r < nb) ? A[(size_t) (k0 + r0 + r) * ld + c] : 0.0;
+#pragma unroll
+                for (int r = 0; r < 16; r++) sacc = fma(lv[r], xk[r0 + r], sacc);
+            }
             ywork[c] -= sacc;
         }
-        __syncthreads();
+        if (kb > 0) {                       // rows of step kb - 1 (a full block: only the last one can be partial)
+            const int k1 = k0 - NB;
+#pragma unroll
+            for (int r = 0; r < NB; r++) l[r] = (tid < k1) ? A[(size_t) (k1 + r) * ld + tid] : 0.0;
+        }
+        // no barrier here: xk is rewritten only behind the next step's first barrier, ys / Li were last read before this step's
+        // second one, and ywork[c] is only ever touched by thread c mod 512
     }
 }
 

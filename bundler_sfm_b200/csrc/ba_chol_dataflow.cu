@@ -65,10 +65,15 @@ __device__ unsigned long long g_df_prof[8];
 __device__ __forceinline__ unsigned long long df_clock() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 __device__ __forceinline__ unsigned long long df_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
 
+// named barriers of CTA 0 (0 = __syncthreads, 2..5 = potf2 panels, see ba_chol_potf2.cuh)
+#define DF_BAR(id, count) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(count) : "memory")
+#define DF_ARRIVE(id, count) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(count) : "memory")
+
 __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A, double *Lout, int ld, int n, double *linv_all, Scalars *sc,
-                                                                     int *ver /* (nbk+1) x (nbk+1) tile versions, init -1 */, int *diag_ready /* nbk, init -1 */, int variant /* dev experiments */)
+                                                                     int *ver /* (nbk+1) x (nbk+1): last step applied to a PUBLISHED tile, init -1 */,
+                                                                     int *diag_ready /* nbk, init -1 */)
 {
-    __shared__ __align__(16) double tiles[5][LNB][TP];      // CTA 0: L_kk, next diagonal tile, X, Z, W;  workers: Z, X_r, X_c
+    __shared__ __align__(16) double tiles[5][LNB][TP];      // CTA 0: L_kk, next diagonal tile, X, Z, W;  workers: Z, 2 x (X_r, X_c)
     __shared__ double dinv[LNB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tg = lane & 3;
@@ -81,9 +86,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
 
     if (blockIdx.x == 0) {
         // ================= the diagonal chain =================
-        // warp 0 factors the diagonal tile (warp_potf2_32_tc), warp 1 assembles its inverse one panel behind, warps 2..7 poll the
-        // flags and fetch the inputs of the look-ahead meanwhile.  Then: X <- X Z^T for the sub-diagonal block (warps 0..3, DMMA)
-        // while warps 4..7 publish L_kk and Z_kk; then the rank-32 update of the next diagonal tile, which never leaves shared memory.
+        // per 32-column step k:
+        //   warp 0       potf2 of the diagonal tile (warp_potf2_32_tc)          warp 1   its inverse Z_kk, one panel behind
+        //   warps 2, 3   poll the flags of the look-ahead inputs -- sub-diagonal block (k+1, k) and diagonal tile (k+1, k+1), both
+        //                through step k-1 -- and fetch them
+        //   warps 4..7   publish L_kk and Z_kk the moment warps 0 / 1 are done (they never wait for the loads)
+        //   warps 0..3   X <- X Z^T for the sub-diagonal block, rank-32 update of the next diagonal tile, which never leaves
+        //                shared memory
         double (*Lc)[TP] = tiles[0], (*Ln)[TP] = tiles[1];
         double (*Xr)[TP] = tiles[2], (*Zs)[TP] = tiles[3], (*Ws)[TP] = tiles[4];
         const unsigned long long ns0 = df_ns();
@@ -102,67 +111,67 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
             const bool last = (k + 1 == nbk);
             const int rb = last ? nbk : k + 1;                 // last step: the right-hand side segment instead of a diagonal tile
             const int rrows = rows_of(rb), rbase = rbase_of(rb);
-            // ---- phase 1: potf2(k) and its inverse  ||  inputs of the look-ahead ----
             tc = df_clock();
-            if (warp == 0) {
-                const bool bad = warp_potf2_32_tc(Lc, dinv, lane, true);
-                if (bad && lane == 0) sc->chol_fail = 1;
-                { const unsigned long long t = df_clock(); pc[0] += t - tc; tc = t; }
-            } else if (warp == 1) {
-                warp_tile_inverse(Lc, dinv, Zs, Ws, lane);
-            } else {
-                if (tid == 64) {
-                    long long spins = 0;
-                    while (ld_acquire(&ver[rb * VW + k]) < k - 1 || (!last && ld_acquire(&ver[rb * VW + rb]) < k - 1)) {
-                        if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
-                        __nanosleep(20);
-                    }
-                }
-                asm volatile("bar.sync 1, 192;" ::: "memory");
-                for (int e = tid - 64; e < LNB * LNB; e += DF_THREADS - 64) {
-                    const int r = e >> 5, c = e & 31;
-                    Xr[r][c] = (r < rrows && c < nb) ? __ldcg(&A[(size_t) (rbase + r) * ld + (k0 + c)]) : 0.0;
-                    if (!last) Ln[r][c] = (r < rrows && c <= r) ? __ldcg(&A[(size_t) (rbase + r) * ld + (rbase + c)]) : ((r == c) ? 1.0 : 0.0);
-                }
-            }
-            __syncthreads();
-            { const unsigned long long t = df_clock(); pc[1] += t - tc; tc = t; }
-            // ---- phase 2: sub-diagonal block X <- X Z^T  ||  publish L_kk and Z_kk ----
-            const int role = (variant & 4) ? (warp ^ 4) : warp;          // dev: swap which half solves and which half publishes
-            if (role < 4) {
-                warp_rows_times_ZT(Xr, 8 * role, Zs, lane);
-                { const unsigned long long t = df_clock(); pc[2] += t - tc; tc = t; }
-            } else {
-                for (int e = (tid ^ ((variant & 4) ? 128 : 0)) - 128; e < LNB * LNB; e += 128) {
+            if (warp >= 4) {
+                // ---- publishers ----
+                DF_BAR(7, 192);                                 // potf2 and inverse done
+                // the workers consume Z_kk only: it goes out first, the release (which carries the fence, cumulative over the
+                // barrier) follows at once; L_kk itself is only read by the back substitution
+                for (int e = tid - 128; e < LNB * LNB; e += 128) linv_all[(size_t) k * LNB * LNB + e] = ((e & 31) <= (e >> 5)) ? Zs[e >> 5][e & 31] : 0.0;
+                DF_BAR(6, 128);
+                if (tid == 128) st_release(&diag_ready[k], 1);
+                for (int e = tid - 128; e < LNB * LNB; e += 128) {
                     const int r = e >> 5, c = e & 31;
                     if (r < nb && c <= r) Lout[(size_t) (k0 + r) * ld + (k0 + c)] = Lc[r][c];
-                    linv_all[(size_t) k * LNB * LNB + e] = (c <= r) ? Zs[r][c] : 0.0;
                 }
-                asm volatile("bar.sync 6, 128;" ::: "memory");
-                if (tid == ((variant & 4) ? 0 : ((variant & 1) ? 224 : 128))) {      // one cumulative fence after the barrier, not 128
-                    if (variant & 2) *reinterpret_cast<volatile int *>(&diag_ready[k]) = 1;        // dev: timing without the fence (NOT correct)
-                    else { __threadfence(); st_release(&diag_ready[k], 1); }
+            } else {
+                if (warp == 0) {
+                    const bool bad = warp_potf2_32_tc(Lc, dinv, lane, true);
+                    if (bad && lane == 0) sc->chol_fail = 1;
+                    __syncwarp();
+                    { const unsigned long long t = df_clock(); pc[0] += t - tc; tc = t; }
+                    DF_ARRIVE(7, 192);
+                } else if (warp == 1) {
+                    warp_tile_inverse(Lc, dinv, Zs, Ws, lane);
+                    DF_ARRIVE(7, 192);
+                } else {
+                    if (tid == 64) {
+                        long long spins = 0;
+                        while (ld_acquire(&ver[rb * VW + k]) < k - 1 || (!last && ld_acquire(&ver[rb * VW + rb]) < k - 1)) {
+                            if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
+                            __nanosleep(20);
+                        }
+                    }
+                    DF_BAR(1, 64);
+                    for (int e = tid - 64; e < LNB * LNB; e += 64) {
+                        const int r = e >> 5, c = e & 31;
+                        Xr[r][c] = (r < rrows && c < nb) ? __ldcg(&A[(size_t) (rbase + r) * ld + (k0 + c)]) : 0.0;
+                        if (!last) Ln[r][c] = (r < rrows && c <= r) ? __ldcg(&A[(size_t) (rbase + r) * ld + (rbase + c)]) : ((r == c) ? 1.0 : 0.0);
+                    }
                 }
-            }
-            __syncthreads();
-            { const unsigned long long t = df_clock(); pc[3] += t - tc; tc = t; }
-            // ---- phase 3: factor block out, rank-32 update of the next diagonal tile (stays in shared memory) ----
-            for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-                const int r = e >> 5, c = e & 31;
-                if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
-            }
-            if (!last) {
-                for (int t = warp; t < 10; t += DF_THREADS / 32) {       // lower 8 x 8 tiles (ri, cj)
-                    int ri = 0, rem = t;
-                    while (rem > ri) { rem -= ri + 1; ri++; }
-                    const int cj = rem;
-                    double c0 = 0.0, c1 = 0.0;
+                DF_BAR(8, 128);                                 // factor, inverse and look-ahead inputs are in shared memory
+                { const unsigned long long t = df_clock(); pc[1] += t - tc; tc = t; }
+                warp_rows_times_ZT(Xr, 8 * warp, Zs, lane);
+                DF_BAR(8, 128);
+                { const unsigned long long t = df_clock(); pc[2] += t - tc; tc = t; }
+                for (int e = tid; e < LNB * LNB; e += 128) {
+                    const int r = e >> 5, c = e & 31;
+                    if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
+                }
+                if (!last) {
+                    for (int t = warp; t < 10; t += 4) {       // lower 8 x 8 tiles (ri, cj)
+                        int ri = 0, rem = t;
+                        while (rem > ri) { rem -= ri + 1; ri++; }
+                        const int cj = rem;
+                        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-                    for (int ks = 0; ks < LNB; ks += 4) tile_dmma(c0, c1, Xr[8 * ri + g][ks + tg], Xr[8 * cj + g][ks + tg]);
-                    double2 cur = *reinterpret_cast<const double2 *>(&Ln[8 * ri + g][8 * cj + 2 * tg]);
-                    cur.x -= c0; cur.y -= c1;
-                    *reinterpret_cast<double2 *>(&Ln[8 * ri + g][8 * cj + 2 * tg]) = cur;
+                        for (int ks = 0; ks < LNB; ks += 4) tile_dmma(c0, c1, Xr[8 * ri + g][ks + tg], Xr[8 * cj + g][ks + tg]);
+                        double2 cur = *reinterpret_cast<const double2 *>(&Ln[8 * ri + g][8 * cj + 2 * tg]);
+                        cur.x -= c0; cur.y -= c1;
+                        *reinterpret_cast<double2 *>(&Ln[8 * ri + g][8 * cj + 2 * tg]) = cur;
+                    }
                 }
+                { const unsigned long long t = df_clock(); pc[3] += t - tc; tc = t; }
             }
             __syncthreads();
             { const unsigned long long t = df_clock(); pc[4] += t - tc; tc = t; }
@@ -177,66 +186,126 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
         return;
     }
 
-    // ================= workers: static tile ownership =================
-    double (*Zs)[TP] = tiles[0], (*Xr)[TP] = tiles[1], (*Xc)[TP] = tiles[2];
-    // load block (rb, cb) of A (rows x width, zero padded) into smem
-    auto load_block = [&](double (*dst)[TP], int rb, int cb, int width) {
-        const int rows = rows_of(rb), rbase = rbase_of(rb), c0 = cb * LNB;
-        for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-            const int r = e >> 5, c = e & 31;
-            dst[r][c] = (r < rows && c < width) ? __ldcg(&A[(size_t) (rbase + r) * ld + (c0 + c)]) : 0.0;     // L2: written by another SM
-        }
-    };
+    // ================= workers: static tile ownership, the owned tiles live in REGISTERS =================
+    // Tile (rb, cb) (1 <= cb < nbk, cb <= rb <= nbk; row block nbk = right-hand side) takes the rank-32 updates of steps
+    // k = 0 .. klast (klast = cb - 1; cb - 2 for a diagonal tile, whose step cb - 1 is CTA 0's look-ahead) and is read by other CTAs
+    // only after that: it is written to global memory and published exactly once.  Each CTA owns at most two tiles (DMMA accumulator
+    // layout: warp w holds the 8 x 8 sub-tiles 2 w, 2 w + 1).  Per step: fetch the two panel blocks of every owned tile (final since
+    // step k - 1) BEFORE the wait for Z_kk, then X <- X Z^T strips and the update, all on the fp64 tensor cores.
+    double (*Zs)[TP] = tiles[0];
     const int w = (int) blockIdx.x - 1;
-    for (int k = 0; k + 1 <= nbk; k++) {
+    int ntile = 0;
+    for (int c = 1; c < nbk; c++) ntile += nbk - c + 1;
+    int trb[2], tcb[2], klast[2];
+    double cur[2][2][2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int ti = w + s * workers;
+        trb[s] = tcb[s] = 0; klast[s] = -1;
+        if (ti < ntile) {
+            int c = 1, rem = ti;
+            while (rem >= nbk - c + 1) { rem -= nbk - c + 1; c++; }
+            tcb[s] = c; trb[s] = c + rem;
+            klast[s] = (trb[s] == c) ? c - 2 : c - 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int t = warp * 2 + i, r = 8 * (t >> 2) + g, c = 8 * (t & 3) + 2 * tg;
+            cur[s][i][0] = cur[s][i][1] = 0.0;
+            if (klast[s] >= 0) {
+                const int rrows = rows_of(trb[s]), crows = rows_of(tcb[s]);
+                const double *src = &A[(size_t) (rbase_of(trb[s]) + r) * ld + (tcb[s] * LNB + c)];
+                if (r < rrows && c < crows) cur[s][i][0] = src[0];
+                if (r < rrows && c + 1 < crows) cur[s][i][1] = src[1];
+            }
+        }
+    }
+    const int kend = max(klast[0], klast[1]);
+    for (int k = 0; k <= kend; k++) {
         const int k0 = k * LNB, nb = min(LNB, n - k0);
-        bool have_z = false;
-        // tiles (rb, cb), k < cb <= rb <= nbk, cb < nbk, owned by this CTA; (k+1, k+1) belongs to CTA 0 at this step
-        for (int cb = k + 1; cb < nbk; cb++) {
-            for (int rb = cb; rb <= nbk; rb++) {
-                if (df_tile_index(rb, cb, nbk) % workers != w) continue;
-                if (rb == cb && cb == k + 1) continue;
-                if (!have_z) {
-                    df_wait(&diag_ready[k], 1, sc);
-                    for (int e = tid; e < LNB * LNB; e += DF_THREADS) Zs[e >> 5][e & 31] = __ldcg(&linv_all[(size_t) k * LNB * LNB + e]);
-                    have_z = true;
+        // (a) the panel blocks of the owned tiles: final since step k - 1
+        if (tid == 0) {
+            long long spins = 0;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                if (k > klast[s]) continue;
+                while (ld_acquire(&ver[trb[s] * VW + k]) < k - 1 || ld_acquire(&ver[tcb[s] * VW + k]) < k - 1) {
+                    if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
+                    __nanosleep(20);
                 }
-                df_wait(&ver[rb * VW + k], k - 1, sc);
-                if (cb != rb) df_wait(&ver[cb * VW + k], k - 1, sc);
-                if (rb == cb && k > 0) df_wait(&ver[rb * VW + cb], k - 1, sc);   // diagonal tiles change hands (CTA 0 did step cb-1 only, but be safe)
-                load_block(Xr, rb, k, nb);
-                if (cb != rb) load_block(Xc, cb, k, nb);
-                __syncthreads();
-                const int rrows = rows_of(rb), crows = rows_of(cb);
-                // both panel blocks: X <- X Z^T, one 8-row strip per warp
-                if (warp < 4) warp_rows_times_ZT(Xr, 8 * warp, Zs, lane);
-                else if (cb != rb) warp_rows_times_ZT(Xc, 8 * (warp - 4), Zs, lane);
-                __syncthreads();
-                const double (*XC)[TP] = (cb != rb) ? Xc : Xr;
-                const int rbase = rbase_of(rb), c0 = cb * LNB;
-                if (cb == k + 1) {          // first column: this tile's row block of the factor
-                    for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-                        const int r = e >> 5, c = e & 31;
-                        if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
-                    }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (k > klast[s]) continue;
+            double (*Xr)[TP] = tiles[1 + 2 * s], (*Xc)[TP] = tiles[2 + 2 * s];
+            const int rrows = rows_of(trb[s]), crows = rows_of(tcb[s]), rbase = rbase_of(trb[s]), cbase = tcb[s] * LNB;
+            for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
+                const int r = e >> 5, c = e & 31;
+                Xr[r][c] = (r < rrows && c < nb) ? __ldcg(&A[(size_t) (rbase + r) * ld + (k0 + c)]) : 0.0;       // L2: written by another SM
+                if (trb[s] != tcb[s]) Xc[r][c] = (r < crows && c < nb) ? __ldcg(&A[(size_t) (cbase + r) * ld + (k0 + c)]) : 0.0;
+            }
+        }
+        // (b) Z_kk
+        if (tid == 0) {
+            long long spins = 0;
+            while (ld_acquire(&diag_ready[k]) < 1) {
+                if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
+                __nanosleep(20);
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < LNB * LNB; e += DF_THREADS) Zs[e >> 5][e & 31] = __ldcg(&linv_all[(size_t) k * LNB * LNB + e]);
+        __syncthreads();
+        // (c) X <- X Z^T: up to 16 eight-row strips, two per warp
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int which = (warp >> 2) & 1, strip = warp & 3;          // slot j: warps 0..3 its row block, warps 4..7 its column block
+            if (k > klast[j] || (which == 1 && trb[j] == tcb[j])) continue;
+            warp_rows_times_ZT(tiles[1 + 2 * j + which], 8 * strip, Zs, lane);
+        }
+        __syncthreads();
+        bool publish = false;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (k > klast[s]) continue;
+            const double (*Xr)[TP] = tiles[1 + 2 * s];
+            const double (*XC)[TP] = (trb[s] != tcb[s]) ? tiles[2 + 2 * s] : tiles[1 + 2 * s];
+            const int rrows = rows_of(trb[s]), crows = rows_of(tcb[s]), rbase = rbase_of(trb[s]), cbase = tcb[s] * LNB;
+            if (tcb[s] == k + 1) {          // first column: this tile's row block of the factor
+                for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
+                    const int r = e >> 5, c = e & 31;
+                    if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
                 }
-                // tile -= X_r X_c^T : sixteen 8 x 8 DMMA tiles, two per warp
+            }
+            // (e) tile -= X_r X_c^T
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int t = warp * 2 + i, ri = t >> 2, cj = t & 3;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < LNB; ks += 4) tile_dmma(a0, a1, Xr[8 * ri + g][ks + tg], XC[8 * cj + g][ks + tg]);
+                cur[s][i][0] -= a0; cur[s][i][1] -= a1;
+            }
+            // (f) final: out to global memory, once
+            if (k == klast[s]) {
+                publish = true;
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const int t = warp * 2 + i, ri = t >> 2, cj = t & 3;
-                    if (rb == cb && cj > ri) continue;
-                    if (8 * ri >= rrows || 8 * cj >= crows) continue;
-                    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks < LNB; ks += 4) tile_dmma(a0, a1, Xr[8 * ri + g][ks + tg], XC[8 * cj + g][ks + tg]);
-                    const int r = 8 * ri + g, c = 8 * cj + 2 * tg;
-                    double *dst = &A[(size_t) (rbase + r) * ld + (c0 + c)];
-                    if (r < rrows && c < crows && (rb != cb || c <= r)) dst[0] = __ldcg(dst) - a0;
-                    if (r < rrows && c + 1 < crows && (rb != cb || c + 1 <= r)) dst[1] = __ldcg(dst + 1) - a1;
+                    const int t = warp * 2 + i, r = 8 * (t >> 2) + g, c = 8 * (t & 3) + 2 * tg;
+                    double *dst = &A[(size_t) (rbase + r) * ld + (cbase + c)];
+                    const bool dg = (trb[s] == tcb[s]);                 // diagonal tile: lower triangle only
+                    if (r < rrows && c < crows && (!dg || c <= r)) dst[0] = cur[s][i][0];
+                    if (r < rrows && c + 1 < crows && (!dg || c + 1 <= r)) dst[1] = cur[s][i][1];
                 }
-                __syncthreads();
-                if (tid == 0) { __threadfence(); st_release(&ver[rb * VW + cb], k); }
             }
+        }
+        __syncthreads();                    // the X buffers are free again; the tile stores are issued
+        if (publish && tid == 0) {          // st.release carries the fence (cumulative over the barrier above)
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+                if (k == klast[s]) st_release(&ver[trb[s] * VW + tcb[s]], k);
         }
     }
 }
@@ -274,16 +343,14 @@ int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double 
     for (int c = 1; c < nbk; c++) ntile += nbk - c + 1;
     static const int grid_cap = []() { const char *e = getenv("BSFM_DF_GRID"); return e ? atoi(e) : 1 << 20; }();      // dev experiments
     const int grid = std::min(grid_cap, std::min(sm_count[dev].load(), 1 + std::max(1, ntile)));
-    if (grid < 2) return BSFM_OK;
+    if (grid < 2 || ntile > 2 * (grid - 1)) return BSFM_OK;      // every worker keeps at most two tiles in registers
     // flags live behind the back-substitution scratch of the workspace (chol_extra_ws_doubles leaves > 64k doubles there)
     double *ywork = linv_ws + (size_t) nbk * LNB * LNB;
     int *flags = reinterpret_cast<int *>(ywork + n + 64);
     int *ver = flags, *diag_ready = flags + (nbk + 1) * (nbk + 1);
     BSFM_CUDA_TRY(cudaMemsetAsync(flags, 0xFF, (size_t) ((nbk + 1) * (nbk + 1) + nbk + 8) * sizeof(int), st));
     int ld = n;
-    static const int variant = []() { const char *e = getenv("BSFM_DF_VARIANT"); return e ? atoi(e) : 0; }();
-    int var = variant;
-    void *args[] = {&A, &Lmat, &ld, &n, &linv_ws, &sc, &ver, &diag_ready, &var};
+    void *args[] = {&A, &Lmat, &ld, &n, &linv_ws, &sc, &ver, &diag_ready};
     BSFM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *) chol_dataflow_kernel, dim3(grid), dim3(DF_THREADS), args, 0, st));
     count_launch();
     chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, ld, n, linv_ws, x, ywork);

@@ -1,9 +1,9 @@
 // ba_chol_potf2.cuh -- the 32 x 32 tile primitives of every dense solve of the BA path (reference: dpotf2 / dtrsm inside dpotrf,
-// lib/sba-1.5/sba_lapack.c:429).  Measured on B200 (profiles/r2_chol_dataflow_v2_cta0_cycles.log): a vector fp64 instruction
-// (DFMA / DMUL / DSETP) issues once per ~16 cycles per SM sub-partition, so a 32-pivot factorisation written with scalar FMAs is
-// bound by its fp64 INSTRUCTION COUNT (13.2k cycles, of which 6k were the rank-8 updates inside the tile) and a thread-per-row
-// triangular solve costs 8.3k cycles.  The fp64 tensor-core instruction (DMMA, mma.sync.m8n8k4.f64) does 256 FMAs per issue slot,
-// so everything that is not the pivot chain itself goes through it:
+// lib/sba-1.5/sba_lapack.c:429).  Measured on B200 (profiles/r2_fp64_issue_rates.log): a vector DFMA issues every 2 cycles per SM
+// sub-partition, a DMMA (mma.sync.m8n8k4.f64, 256 FMAs) every 16 -- the same peak FLOP rate, but one instruction instead of eight
+// plus the shuffles / shared-memory loads that feed them.  The 32-pivot chain is LATENCY bound (shuffle -> rsqrt -> multiply ->
+// update, ~240 cycles per pivot), so everything that is not the chain itself is taken off the factoring warp or batched into DMMAs
+// (profiles/r2_chol_dataflow_v2_cta0_cycles.log -> r2_chol_dataflow_v3_regtiles.log: 13.2k -> 7.7k cycles per tile):
 //   warp_potf2_32_tc   one warp: four 8-column register panels (pivots / multipliers by shuffle, reciprocal square root as a
 //                      MUFU seed + one cubic correction, validity test on the integer pipe), the rank-8 update of the columns to
 //                      the right as DMMA tiles; signals a named barrier after every panel

@@ -86,3 +86,55 @@ extern "C" double bsfm_measure_int8_peak(int n_tile, int iters)
     const double ops = (double) sms * iters * 4.0 * (128.0 * n_tile * 32.0) * 2.0;
     return ops / (ms * 1e-3) / 1e12;
 }
+
+// ---- fp64 issue rates (dev measurement behind DESIGN.md's notes on the Cholesky pivot chain) ----
+// mode 0: vector DFMA, 8 independent chains per thread;  mode 1: DMMA m8n8k4, 4 independent accumulator pairs per thread.
+// One CTA per SM, `warps` warps; returns SM cycles per warp instruction per SM sub-partition (warps spread over the 4 of them).
+namespace bsfm {
+__global__ void fp64_rate_kernel(int iters, int mode, double *sink, unsigned long long *cycles)
+{
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double b = 1.0 + 1e-12 * threadIdx.x, c = 1e-13;
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+    if (mode == 0) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = fma(a[i], b, c);
+        }
+    } else {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(a[i]), "+d"(a[i + 1]) : "d"(b), "d"(c));
+        }
+    }
+    const unsigned long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 12345.678) sink[0] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+}  // namespace bsfm
+
+extern "C" double bsfm_measure_fp64_issue_cycles(int mode, int warps, int iters)
+{
+    using namespace bsfm;
+    clear_error();
+    if (require_device() != BSFM_OK) return -1.0;
+    if (warps < 1 || warps > 32 || iters < 16 || (mode != 0 && mode != 1)) { set_error("bsfm_measure_fp64_issue_cycles: bad arguments"); return -1.0; }
+    double *sink = nullptr; unsigned long long *cyc = nullptr, h = 0;
+    if (cudaMalloc(&sink, 8) != cudaSuccess || cudaMalloc(&cyc, 8) != cudaSuccess) { set_error("cudaMalloc failed"); return -1.0; }
+    fp64_rate_kernel<<<1, 32 * warps>>>(iters, mode, sink, cyc);
+    fp64_rate_kernel<<<1, 32 * warps>>>(iters, mode, sink, cyc);
+    count_launch(2);
+    const cudaError_t e = cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    cudaFree(sink); cudaFree(cyc);
+    if (e != cudaSuccess) { set_error("bsfm_measure_fp64_issue_cycles: %s", cudaGetErrorString(e)); return -1.0; }
+    const double instr_per_warp = (double) iters * (mode == 0 ? 8.0 : 4.0);
+    const double warps_per_smsp = (warps + 3) / 4;
+    return (double) h / (instr_per_warp * warps_per_smsp);
+}

@@ -28,27 +28,50 @@ namespace ba {
 constexpr int DF_THREADS = 256;
 constexpr long long DF_SPIN_LIMIT = 400000;      // polls of ~0.5-1 us: a lost flag costs well under a second, never a hang
 
-__device__ __forceinline__ int ld_acquire(const int *p)
+// ---- data that is its own "ready" flag ----
+// Everything that travels between CTAs (Z_kk blocks, finished tiles) is written exactly once per solve into memory the host
+// pre-filled with an all-ones pattern (a NaN no arithmetic produces).  A consumer simply re-reads each 8-byte word until it is not
+// the pattern: naturally aligned 8-byte accesses are single-copy atomic, so a word is either "not yet" or final.  Compared with a
+// separate flag this removes one L2 round trip and the fence on each side of every hop (store, fence, flag | poll, load).
+__device__ __forceinline__ double ld_strong(const double *p)
 {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v)
+__device__ __forceinline__ void st_strong(double *p, double v)
 {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-// thread 0 polls until *flag >= need (bounded); the CTA continues after the barrier
-__device__ __forceinline__ void df_wait(const int *flag, int need, Scalars *sc)
+__device__ __forceinline__ bool df_pending(double v) { return __double_as_longlong(v) == -1LL; }
+
+// Fetch NE elements per thread: element i of this thread comes from src(i) (nullptr: not part of the tile, takes fill(i)) and is
+// handed to put(i, value).  Re-reads the words that are still pending (bounded).
+template <int NE, class Src, class Put>
+__device__ __forceinline__ void df_fetch(Src src, Put put, Scalars *sc)
 {
-    if (threadIdx.x == 0) {
-        long long spins = 0;
-        while (ld_acquire(flag) < need) {
-            if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
-            __nanosleep(40);
-        }
+    double v[NE];
+    unsigned pend = 0;
+#pragma unroll
+    for (int i = 0; i < NE; i++) {
+        const double *p = src(i);
+        v[i] = p ? ld_strong(p) : 0.0;
+        if (p && df_pending(v[i])) pend |= 1u << i;
     }
-    __syncthreads();
+    long long spins = 0;
+    while (pend) {
+#pragma unroll
+        for (int i = 0; i < NE; i++) {
+            if (pend & (1u << i)) {
+                v[i] = ld_strong(src(i));
+                if (!df_pending(v[i])) pend &= ~(1u << i);
+            }
+        }
+        if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
+        if (pend) __nanosleep(32);
+    }
+#pragma unroll
+    for (int i = 0; i < NE; i++) put(i, v[i]);
 }
 
 // tile index of (rb, cb), 1 <= cb <= rb <= nbk (block row nbk = right-hand side), column-major over cb
@@ -69,16 +92,14 @@ __device__ __forceinline__ unsigned long long df_ns() { unsigned long long t; as
 #define DF_BAR(id, count) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(count) : "memory")
 #define DF_ARRIVE(id, count) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(count) : "memory")
 
-__global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A, double *Lout, int ld, int n, double *linv_all, Scalars *sc,
-                                                                     int *ver /* (nbk+1) x (nbk+1): last step applied to a PUBLISHED tile, init -1 */,
-                                                                     int *diag_ready /* nbk, init -1 */)
+__global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(const double *A, double *Lout, int ld, int n, double *linv_all /* pre-filled */,
+                                                                     double *Pub /* (n + 1) x n finished tiles, pre-filled */, Scalars *sc)
 {
     __shared__ __align__(16) double tiles[5][LNB][TP];      // CTA 0: L_kk, next diagonal tile, X, Z, W;  workers: Z, 2 x (X_r, X_c)
     __shared__ double dinv[LNB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tg = lane & 3;
     const int nbk = (n + LNB - 1) / LNB;
-    const int VW = nbk + 1;                  // row pitch of `ver`
     const int workers = (int) gridDim.x - 1;
 
     auto rows_of = [&](int rb) { return (rb == nbk) ? 1 : min(LNB, n - rb * LNB); };
@@ -88,9 +109,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
         // ================= the diagonal chain =================
         // per 32-column step k:
         //   warp 0       potf2 of the diagonal tile (warp_potf2_32_tc)          warp 1   its inverse Z_kk, one panel behind
-        //   warps 2, 3   poll the flags of the look-ahead inputs -- sub-diagonal block (k+1, k) and diagonal tile (k+1, k+1), both
-        //                through step k-1 -- and fetch them
-        //   warps 4..7   publish L_kk and Z_kk the moment warps 0 / 1 are done (they never wait for the loads)
+        //   warps 2, 3   fetch the look-ahead inputs -- sub-diagonal block (k+1, k) and diagonal tile (k+1, k+1), both finished by
+        //                their owners with step k-1 -- as soon as their words arrive
+        //   warps 4..7   send Z_kk out the moment warps 0 / 1 are done (they never wait for the loads), then L_kk
         //   warps 0..3   X <- X Z^T for the sub-diagonal block, rank-32 update of the next diagonal tile, which never leaves
         //                shared memory
         double (*Lc)[TP] = tiles[0], (*Ln)[TP] = tiles[1];
@@ -113,13 +134,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
             const int rrows = rows_of(rb), rbase = rbase_of(rb);
             tc = df_clock();
             if (warp >= 4) {
-                // ---- publishers ----
+                // ---- senders ----
                 DF_BAR(7, 192);                                 // potf2 and inverse done
-                // the workers consume Z_kk only: it goes out first, the release (which carries the fence, cumulative over the
-                // barrier) follows at once; L_kk itself is only read by the back substitution
-                for (int e = tid - 128; e < LNB * LNB; e += 128) linv_all[(size_t) k * LNB * LNB + e] = ((e & 31) <= (e >> 5)) ? Zs[e >> 5][e & 31] : 0.0;
-                DF_BAR(6, 128);
-                if (tid == 128) st_release(&diag_ready[k], 1);
+                for (int e = tid - 128; e < LNB * LNB; e += 128) st_strong(&linv_all[(size_t) k * LNB * LNB + e], ((e & 31) <= (e >> 5)) ? Zs[e >> 5][e & 31] : 0.0);
                 for (int e = tid - 128; e < LNB * LNB; e += 128) {
                     const int r = e >> 5, c = e & 31;
                     if (r < nb && c <= r) Lout[(size_t) (k0 + r) * ld + (k0 + c)] = Lc[r][c];
@@ -135,18 +152,18 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
                     warp_tile_inverse(Lc, dinv, Zs, Ws, lane);
                     DF_ARRIVE(7, 192);
                 } else {
-                    if (tid == 64) {
-                        long long spins = 0;
-                        while (ld_acquire(&ver[rb * VW + k]) < k - 1 || (!last && ld_acquire(&ver[rb * VW + rb]) < k - 1)) {
-                            if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
-                            __nanosleep(20);
-                        }
-                    }
-                    DF_BAR(1, 64);
-                    for (int e = tid - 64; e < LNB * LNB; e += 64) {
-                        const int r = e >> 5, c = e & 31;
-                        Xr[r][c] = (r < rrows && c < nb) ? __ldcg(&A[(size_t) (rbase + r) * ld + (k0 + c)]) : 0.0;
-                        if (!last) Ln[r][c] = (r < rrows && c <= r) ? __ldcg(&A[(size_t) (rbase + r) * ld + (rbase + c)]) : ((r == c) ? 1.0 : 0.0);
+                    const double *src = (k == 0) ? A : Pub;     // step 0 reads the untouched input
+                    const int t64 = tid - 64;
+#pragma unroll 1
+                    for (int e0 = 0; e0 < LNB * LNB; e0 += 64 * 8) {
+                        df_fetch<8>([&](int i) -> const double * { const int e = e0 + t64 + 64 * i, r = e >> 5, c = e & 31;
+                                                                   return (r < rrows && c < nb) ? &src[(size_t) (rbase + r) * ld + (k0 + c)] : nullptr; },
+                                    [&](int i, double v) { const int e = e0 + t64 + 64 * i; Xr[e >> 5][e & 31] = v; }, sc);
+                        if (!last)
+                            df_fetch<8>([&](int i) -> const double * { const int e = e0 + t64 + 64 * i, r = e >> 5, c = e & 31;
+                                                                       return (r < rrows && c <= r) ? &src[(size_t) (rbase + r) * ld + (rbase + c)] : nullptr; },
+                                        [&](int i, double v) { const int e = e0 + t64 + 64 * i, r = e >> 5, c = e & 31;
+                                                               Ln[r][c] = (r < rrows && c <= r) ? v : ((r == c) ? 1.0 : 0.0); }, sc);
                     }
                 }
                 DF_BAR(8, 128);                                 // factor, inverse and look-ahead inputs are in shared memory
@@ -189,9 +206,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
     // ================= workers: static tile ownership, the owned tiles live in REGISTERS =================
     // Tile (rb, cb) (1 <= cb < nbk, cb <= rb <= nbk; row block nbk = right-hand side) takes the rank-32 updates of steps
     // k = 0 .. klast (klast = cb - 1; cb - 2 for a diagonal tile, whose step cb - 1 is CTA 0's look-ahead) and is read by other CTAs
-    // only after that: it is written to global memory and published exactly once.  Each CTA owns at most two tiles (DMMA accumulator
-    // layout: warp w holds the 8 x 8 sub-tiles 2 w, 2 w + 1).  Per step: fetch the two panel blocks of every owned tile (final since
-    // step k - 1) BEFORE the wait for Z_kk, then X <- X Z^T strips and the update, all on the fp64 tensor cores.
+    // only after that: it goes out to `Pub` exactly once.  Each CTA owns at most two tiles (DMMA accumulator layout: warp w holds
+    // the 8 x 8 sub-tiles 2 w, 2 w + 1).  Per step: fetch the two panel blocks of every owned tile (finished with step k - 1), then
+    // Z_kk, then X <- X Z^T strips and the update, all on the fp64 tensor cores.
     double (*Zs)[TP] = tiles[0];
     const int w = (int) blockIdx.x - 1;
     int ntile = 0;
@@ -223,40 +240,24 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
     const int kend = max(klast[0], klast[1]);
     for (int k = 0; k <= kend; k++) {
         const int k0 = k * LNB, nb = min(LNB, n - k0);
-        // (a) the panel blocks of the owned tiles: final since step k - 1
-        if (tid == 0) {
-            long long spins = 0;
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                if (k > klast[s]) continue;
-                while (ld_acquire(&ver[trb[s] * VW + k]) < k - 1 || ld_acquire(&ver[tcb[s] * VW + k]) < k - 1) {
-                    if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
-                    __nanosleep(20);
-                }
-            }
-        }
-        __syncthreads();
+        const double *src = (k == 0) ? A : Pub;
+        // (a) the panel blocks of the owned tiles: finished by their owners with step k - 1
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             if (k > klast[s]) continue;
             double (*Xr)[TP] = tiles[1 + 2 * s], (*Xc)[TP] = tiles[2 + 2 * s];
             const int rrows = rows_of(trb[s]), crows = rows_of(tcb[s]), rbase = rbase_of(trb[s]), cbase = tcb[s] * LNB;
-            for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-                const int r = e >> 5, c = e & 31;
-                Xr[r][c] = (r < rrows && c < nb) ? __ldcg(&A[(size_t) (rbase + r) * ld + (k0 + c)]) : 0.0;       // L2: written by another SM
-                if (trb[s] != tcb[s]) Xc[r][c] = (r < crows && c < nb) ? __ldcg(&A[(size_t) (cbase + r) * ld + (k0 + c)]) : 0.0;
-            }
+            df_fetch<4>([&](int i) -> const double * { const int e = tid + DF_THREADS * i, r = e >> 5, c = e & 31;
+                                                       return (r < rrows && c < nb) ? &src[(size_t) (rbase + r) * ld + (k0 + c)] : nullptr; },
+                        [&](int i, double v) { const int e = tid + DF_THREADS * i; Xr[e >> 5][e & 31] = v; }, sc);
+            if (trb[s] != tcb[s])
+                df_fetch<4>([&](int i) -> const double * { const int e = tid + DF_THREADS * i, r = e >> 5, c = e & 31;
+                                                           return (r < crows && c < nb) ? &src[(size_t) (cbase + r) * ld + (k0 + c)] : nullptr; },
+                            [&](int i, double v) { const int e = tid + DF_THREADS * i; Xc[e >> 5][e & 31] = v; }, sc);
         }
         // (b) Z_kk
-        if (tid == 0) {
-            long long spins = 0;
-            while (ld_acquire(&diag_ready[k]) < 1) {
-                if (++spins > DF_SPIN_LIMIT) { sc->chol_fail = 2; break; }
-                __nanosleep(20);
-            }
-        }
-        __syncthreads();
-        for (int e = tid; e < LNB * LNB; e += DF_THREADS) Zs[e >> 5][e & 31] = __ldcg(&linv_all[(size_t) k * LNB * LNB + e]);
+        df_fetch<4>([&](int i) -> const double * { return &linv_all[(size_t) k * LNB * LNB + tid + DF_THREADS * i]; },
+                    [&](int i, double v) { const int e = tid + DF_THREADS * i; Zs[e >> 5][e & 31] = v; }, sc);
         __syncthreads();
         // (c) X <- X Z^T: up to 16 eight-row strips, two per warp
 #pragma unroll
@@ -266,19 +267,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
             warp_rows_times_ZT(tiles[1 + 2 * j + which], 8 * strip, Zs, lane);
         }
         __syncthreads();
-        bool publish = false;
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             if (k > klast[s]) continue;
             const double (*Xr)[TP] = tiles[1 + 2 * s];
             const double (*XC)[TP] = (trb[s] != tcb[s]) ? tiles[2 + 2 * s] : tiles[1 + 2 * s];
             const int rrows = rows_of(trb[s]), crows = rows_of(tcb[s]), rbase = rbase_of(trb[s]), cbase = tcb[s] * LNB;
-            if (tcb[s] == k + 1) {          // first column: this tile's row block of the factor
-                for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
-                    const int r = e >> 5, c = e & 31;
-                    if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
-                }
-            }
             // (e) tile -= X_r X_c^T
 #pragma unroll
             for (int i = 0; i < 2; i++) {
@@ -288,25 +282,25 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(double *A,
                 for (int ks = 0; ks < LNB; ks += 4) tile_dmma(a0, a1, Xr[8 * ri + g][ks + tg], XC[8 * cj + g][ks + tg]);
                 cur[s][i][0] -= a0; cur[s][i][1] -= a1;
             }
-            // (f) final: out to global memory, once
+            // (f) finished: out to the other CTAs, once (the words are their own flags)
             if (k == klast[s]) {
-                publish = true;
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const int t = warp * 2 + i, r = 8 * (t >> 2) + g, c = 8 * (t & 3) + 2 * tg;
-                    double *dst = &A[(size_t) (rbase + r) * ld + (cbase + c)];
+                    double *dst = &Pub[(size_t) (rbase + r) * ld + (cbase + c)];
                     const bool dg = (trb[s] == tcb[s]);                 // diagonal tile: lower triangle only
-                    if (r < rrows && c < crows && (!dg || c <= r)) dst[0] = cur[s][i][0];
-                    if (r < rrows && c + 1 < crows && (!dg || c + 1 <= r)) dst[1] = cur[s][i][1];
+                    if (r < rrows && c < crows && (!dg || c <= r)) st_strong(dst, cur[s][i][0]);
+                    if (r < rrows && c + 1 < crows && (!dg || c + 1 <= r)) st_strong(dst + 1, cur[s][i][1]);
+                }
+            }
+            if (tcb[s] == k + 1) {          // first column: this tile's row block of the factor (read by the back substitution only)
+                for (int e = tid; e < LNB * LNB; e += DF_THREADS) {
+                    const int r = e >> 5, c = e & 31;
+                    if (r < rrows && c < nb) Lout[(size_t) (rbase + r) * ld + (k0 + c)] = Xr[r][c];
                 }
             }
         }
-        __syncthreads();                    // the X buffers are free again; the tile stores are issued
-        if (publish && tid == 0) {          // st.release carries the fence (cumulative over the barrier above)
-#pragma unroll
-            for (int s = 0; s < 2; s++)
-                if (k == klast[s]) st_release(&ver[trb[s] * VW + tcb[s]], k);
-        }
+        __syncthreads();                    // the X buffers are free again
     }
 }
 
@@ -338,19 +332,20 @@ int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double 
     }
     if (coop_ok[dev].load() != 1) return BSFM_OK;
     const int nbk = (n + LNB - 1) / LNB;
-    if (nbk < 2 || nbk > df_max_blocks()) return BSFM_OK;      // larger systems: the workers' serial tile loop loses to the fused-step path
+    if (nbk < 2 || nbk > df_max_blocks() || n > DF_MAX_N) return BSFM_OK;      // larger systems: more than two tiles per worker
     int ntile = 0;
     for (int c = 1; c < nbk; c++) ntile += nbk - c + 1;
     static const int grid_cap = []() { const char *e = getenv("BSFM_DF_GRID"); return e ? atoi(e) : 1 << 20; }();      // dev experiments
     const int grid = std::min(grid_cap, std::min(sm_count[dev].load(), 1 + std::max(1, ntile)));
     if (grid < 2 || ntile > 2 * (grid - 1)) return BSFM_OK;      // every worker keeps at most two tiles in registers
-    // flags live behind the back-substitution scratch of the workspace (chol_extra_ws_doubles leaves > 64k doubles there)
+    // workspace: [Z blocks nbk x 1024][back-substitution scratch n + 64][finished tiles (n + 1) x n]; the Z blocks and the tile
+    // area are pre-filled with the "not yet" pattern (all ones) by one memset
     double *ywork = linv_ws + (size_t) nbk * LNB * LNB;
-    int *flags = reinterpret_cast<int *>(ywork + n + 64);
-    int *ver = flags, *diag_ready = flags + (nbk + 1) * (nbk + 1);
-    BSFM_CUDA_TRY(cudaMemsetAsync(flags, 0xFF, (size_t) ((nbk + 1) * (nbk + 1) + nbk + 8) * sizeof(int), st));
+    double *pub = ywork + n + 64;
+    BSFM_CUDA_TRY(cudaMemsetAsync(linv_ws, 0xFF, ((size_t) nbk * LNB * LNB + n + 64 + (size_t) (n + 1) * n) * sizeof(double), st));
     int ld = n;
-    void *args[] = {&A, &Lmat, &ld, &n, &linv_ws, &sc, &ver, &diag_ready};
+    const double *Ac = A;
+    void *args[] = {&Ac, &Lmat, &ld, &n, &linv_ws, &pub, &sc};
     BSFM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *) chol_dataflow_kernel, dim3(grid), dim3(DF_THREADS), args, 0, st));
     count_launch();
     chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, ld, n, linv_ws, x, ywork);

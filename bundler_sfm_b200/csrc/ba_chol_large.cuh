@@ -54,7 +54,11 @@ int tc_syrk_update(cudaStream_t st, const TcWorkspace &ws, double *A, const doub
 int tc_sm_count();
 int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *xinv_ws, double *x, Scalars *sc, const TcWorkspace *ws);
 // doubles of linear-solver workspace behind the 32 x 32 inverses: back-substitution scratch (small path) or the 256 x 256 panel inverses (large path)
-inline size_t chol_extra_ws_doubles(int n) { return (size_t) ((n + LNBO - 1) / LNBO) * LNBO * LNBO + (size_t) n + 64; }
+constexpr int DF_MAX_N = 24 * LNB;       // largest system the dataflow path (ba_chol_dataflow.cu) takes: it needs (n + 1) x n doubles more
+inline size_t chol_extra_ws_doubles(int n)
+{
+    return (size_t) ((n + LNBO - 1) / LNBO) * LNBO * LNBO + (size_t) n + 64 + (n <= DF_MAX_N ? (size_t) (n + 1) * n + 64 : 0);
+}
 
 __host__ __device__ __forceinline__ size_t tc_slice_offset(int tile, int half, int k, int ns)
 {

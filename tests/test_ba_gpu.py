@@ -230,9 +230,10 @@ def _axb_chol(A, b):
     return fn(A.ctypes.data, b.ctypes.data, x.ctypes.data, A.shape[0], 0), x
 
 
-@pytest.mark.parametrize("n", [9, 450, 1547, 2100, 4000])
+@pytest.mark.parametrize("n", [9, 33, 64, 65, 255, 321, 450, 640, 641, 1547, 2100, 4000])
 def test_axb_chol_vs_lapack(n):
-    """small path (<= 1536) and the 256-column panel path with the tcgen05 int8-slice trailing update (> 1536), incl. an odd
+    """single tile (<= 32), the one-launch dataflow path (<= 640, incl. partial last tiles and the two-tiles-per-CTA regime), the
+    fused-step path (<= 1536) and the 256-column panel path with the tcgen05 int8-slice trailing update (> 1536), incl. an odd
     dimension and one that is not a multiple of 32: backward error at the level of LAPACK's, solution close to LAPACK's"""
     A = _spd(n, seed=n)
     xt = np.random.default_rng(1).standard_normal(n)
@@ -273,6 +274,34 @@ def test_axb_chol_reports_indefinite_matrix(n):
     A = _spd(n, seed=5)
     A[n // 2, n // 2] = -1.0
     rc, _ = _axb_chol(A, np.ones(n))
+    assert rc == 0
+
+
+@pytest.mark.parametrize("n", [97, 450, 640])
+def test_axb_chol_dataflow_equals_fused_step_path(n):
+    """the cooperative dataflow factorisation (ba_chol_dataflow.cu) against the one-launch-per-32-columns path it replaces
+    (BSFM_BA_CHOL_DATAFLOW=0), each in a child process"""
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from tests.test_ba_gpu import _spd, _axb_chol; "
+            "n = int(sys.argv[2]); A = _spd(n, 21); b = A @ np.random.default_rng(4).standard_normal(n); rc, x = _axb_chol(A, b); "
+            "assert rc == 1; np.save(sys.argv[1], x)") % ROOT
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for df in ("1", "0"):
+            f = os.path.join(td, f"x{df}.npy")
+            subprocess.run([sys.executable, "-c", code, f, str(n)], check=True, env=dict(os.environ, BSFM_BA_CHOL_DATAFLOW=df))
+            outs.append(np.load(f))
+    assert np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[1]) <= 1e-7
+
+
+@pytest.mark.parametrize("where", [3, 200, 449])
+def test_axb_chol_dataflow_reports_bad_pivot_anywhere(where):
+    """a non-positive pivot in the first tile, in the middle and in the last (partial) tile of a 450 x 450 system"""
+    A = _spd(450, seed=6)
+    A[where, where] = -1.0
+    rc, _ = _axb_chol(A, np.ones(450))
     assert rc == 0
 
 

@@ -199,21 +199,38 @@ __global__ void __launch_bounds__(256) chol_trsm_kernel(const TrsmArgs T, SliceO
     if (rcount <= 0) return;
     const double *Lfac = T.Lfac;
     const int ld = T.ld;
-    for (int r0 = 0; r0 < TR_ROWS; r0 += 16) {       // thread = column, 16 rows per batch: 16 independent loads in flight
-        double v[16];
+    for (int r0 = 0; r0 < TR_ROWS; r0 += 32) {       // thread = column, 32 rows per batch: 32 independent loads in flight
+        double v[32];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < 32; i++) {
             const int r = r0 + i, c = tid;
             v[i] = 0.0;
             if (r < rcount && c < nb) v[i] = T.ident ? ((row0 + r == c) ? 1.0 : 0.0) : T.A[(size_t) (row0 + r) * ld + (k0 + c)];
         }
 #pragma unroll
-        for (int i = 0; i < 16; i++) Xs[(r0 + i) * TR_LDX + tid] = v[i];
+        for (int i = 0; i < 32; i++) Xs[(r0 + i) * TR_LDX + tid] = v[i];
     }
     if (tid < TR_ROWS) rmax[tid] = 0ull;
     const int nsub = (nb + LNB - 1) / LNB;
     const int wr = warp & 3, wc = warp >> 2;
     const double *xrow0 = Xs + (wr * 16 + g) * TR_LDX, *xrow1 = xrow0 + 8 * TR_LDX;
+    double pre[4 * TR_NLB];      // the blocks of the NEXT sub-step, 4 elements of each per thread
+    auto trsm_prefetch = [&](int sn) {
+        const int wn = min(LNB, nb - sn * LNB);
+#pragma unroll
+        for (int t = 0; t < TR_NLB; t++) {
+            if (t > sn) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = tid + 256 * j, c = e >> 5, u = e & 31;
+                double v = 0.0;
+                if (t < sn) { if (c < wn) v = Lfac[(size_t) (k0 + sn * LNB + c) * ld + (k0 + t * LNB + u)]; }
+                else v = T.linv_all[(size_t) (k0 / LNB + sn) * LNB * LNB + e];
+                pre[4 * t + j] = v;
+            }
+        }
+    };
+    trsm_prefetch(0);
     __syncthreads();
     for (int s = 0; s < nsub; s++) {
         const int w = min(LNB, nb - s * LNB);
@@ -225,26 +242,16 @@ __global__ void __launch_bounds__(256) chol_trsm_kernel(const TrsmArgs T, SliceO
                 const double *src = Xs + (wr * 16 + i * 8 + g) * TR_LDX + s * LNB + wc * 16 + j * 8 + 2 * tg;
                 acc[i][j][0] = src[0]; acc[i][j][1] = src[1];
             }
-        // one staging phase per sub-step (a single L2 round trip): the s blocks L_s0 .. L_s,s-1 and Z_ss
+        // staging: the blocks L_s0 .. L_s,s-1 and Z_ss were requested one sub-step ahead (they depend on nothing computed here),
+        // so their L2 latency hides under the previous sub-step's MMAs instead of costing up to four round trips per sub-step
         __syncthreads();
-        for (int t0 = 0; t0 <= s; t0 += 2) {        // two blocks (8 loads per thread) per batch
-            double v[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int e = t0 * 1024 + tid + 256 * i;
-                const int t = e >> 10, c = (e >> 5) & 31, u = e & 31;
-                v[i] = 0.0;
-                if (t < s) { if (c < w) v[i] = Lfac[(size_t) (k0 + s * LNB + c) * ld + (k0 + t * LNB + u)]; }
-                else if (t == s) v[i] = T.linv_all[(size_t) (k0 / LNB + s) * LNB * LNB + (e & 1023)];
-            }
+        for (int t = 0; t < TR_NLB; t++)
+            if (t <= s)
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int e = t0 * 1024 + tid + 256 * i;
-                const int t = e >> 10;
-                if (t <= s) Lb[t][(e >> 5) & 31][e & 31] = v[i];
-            }
-        }
+                for (int j = 0; j < 4; j++) { const int e = tid + 256 * j; Lb[t][e >> 5][e & 31] = pre[4 * t + j]; }
         __syncthreads();
+        if (s + 1 < nsub) trsm_prefetch(s + 1);
         for (int t = 0; t < s; t++) {
 #pragma unroll
             for (int ks = 0; ks < LNB; ks += 4) {

@@ -93,7 +93,7 @@ __device__ __forceinline__ unsigned long long df_ns() { unsigned long long t; as
 #define DF_ARRIVE(id, count) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(count) : "memory")
 
 __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(const double *A, double *Lout, int ld, int n, double *linv_all /* pre-filled */,
-                                                                     double *Pub /* (n + 1) x n finished tiles, pre-filled */, Scalars *sc)
+                                                                     double *Pub /* (n + 1) x ldp finished tiles, pre-filled */, int ldp, Scalars *sc)
 {
     __shared__ __align__(16) double tiles[5][LNB][TP];      // CTA 0: L_kk, next diagonal tile, X, Z, W;  workers: Z, 2 x (X_r, X_c)
     __shared__ double dinv[LNB];
@@ -153,15 +153,16 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(const doub
                     DF_ARRIVE(7, 192);
                 } else {
                     const double *src = (k == 0) ? A : Pub;     // step 0 reads the untouched input
+                    const int lds = (k == 0) ? ld : ldp;
                     const int t64 = tid - 64;
 #pragma unroll 1
                     for (int e0 = 0; e0 < LNB * LNB; e0 += 64 * 8) {
                         df_fetch<8>([&](int i) -> const double * { const int e = e0 + t64 + 64 * i, r = e >> 5, c = e & 31;
-                                                                   return (r < rrows && c < nb) ? &src[(size_t) (rbase + r) * ld + (k0 + c)] : nullptr; },
+                                                                   return (r < rrows && c < nb) ? &src[(size_t) (rbase + r) * lds + (k0 + c)] : nullptr; },
                                     [&](int i, double v) { const int e = e0 + t64 + 64 * i; Xr[e >> 5][e & 31] = v; }, sc);
                         if (!last)
                             df_fetch<8>([&](int i) -> const double * { const int e = e0 + t64 + 64 * i, r = e >> 5, c = e & 31;
-                                                                       return (r < rrows && c <= r) ? &src[(size_t) (rbase + r) * ld + (rbase + c)] : nullptr; },
+                                                                       return (r < rrows && c <= r) ? &src[(size_t) (rbase + r) * lds + (rbase + c)] : nullptr; },
                                         [&](int i, double v) { const int e = e0 + t64 + 64 * i, r = e >> 5, c = e & 31;
                                                                Ln[r][c] = (r < rrows && c <= r) ? v : ((r == c) ? 1.0 : 0.0); }, sc);
                     }
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(const doub
     for (int k = 0; k <= kend; k++) {
         const int k0 = k * LNB, nb = min(LNB, n - k0);
         const double *src = (k == 0) ? A : Pub;
+        const int lds = (k == 0) ? ld : ldp;
         // (a) the panel blocks of the owned tiles: finished by their owners with step k - 1
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -248,11 +250,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(const doub
             double (*Xr)[TP] = tiles[1 + 2 * s], (*Xc)[TP] = tiles[2 + 2 * s];
             const int rrows = rows_of(trb[s]), crows = rows_of(tcb[s]), rbase = rbase_of(trb[s]), cbase = tcb[s] * LNB;
             df_fetch<4>([&](int i) -> const double * { const int e = tid + DF_THREADS * i, r = e >> 5, c = e & 31;
-                                                       return (r < rrows && c < nb) ? &src[(size_t) (rbase + r) * ld + (k0 + c)] : nullptr; },
+                                                       return (r < rrows && c < nb) ? &src[(size_t) (rbase + r) * lds + (k0 + c)] : nullptr; },
                         [&](int i, double v) { const int e = tid + DF_THREADS * i; Xr[e >> 5][e & 31] = v; }, sc);
             if (trb[s] != tcb[s])
                 df_fetch<4>([&](int i) -> const double * { const int e = tid + DF_THREADS * i, r = e >> 5, c = e & 31;
-                                                           return (r < crows && c < nb) ? &src[(size_t) (cbase + r) * ld + (k0 + c)] : nullptr; },
+                                                           return (r < crows && c < nb) ? &src[(size_t) (cbase + r) * lds + (k0 + c)] : nullptr; },
                             [&](int i, double v) { const int e = tid + DF_THREADS * i; Xc[e >> 5][e & 31] = v; }, sc);
         }
         // (b) Z_kk
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) chol_dataflow_kernel(const doub
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const int t = warp * 2 + i, r = 8 * (t >> 2) + g, c = 8 * (t & 3) + 2 * tg;
-                    double *dst = &Pub[(size_t) (rbase + r) * ld + (cbase + c)];
+                    double *dst = &Pub[(size_t) (rbase + r) * ldp + (cbase + c)];
                     const bool dg = (trb[s] == tcb[s]);                 // diagonal tile: lower triangle only
                     if (r < rrows && c < crows && (!dg || c <= r)) st_strong(dst, cur[s][i][0]);
                     if (r < rrows && c + 1 < crows && (!dg || c + 1 <= r)) st_strong(dst + 1, cur[s][i][1]);
@@ -312,8 +314,10 @@ static int df_max_blocks()
     return v;
 }
 
-// *used = false: not usable here (caller falls back to the fused-step path); else launched
-int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *x, Scalars *sc, bool *used)
+// Factorisation only: A (pitch ld, n x n lower + right-hand side row n) -> Lmat (same pitch), inverses of the 32 x 32 diagonal blocks
+// -> linv_blocks[k * 1024].  pub: (n + 1) x n doubles of scratch.  A and Lmat may point INTO a larger matrix (the large path
+// finishes its last panels with this kernel).  *used = false: not usable here (caller falls back), nothing launched.
+int chol_dataflow_factor(cudaStream_t st, const double *A, double *Lmat, int ld, int n, double *linv_blocks, double *pub, Scalars *sc, bool *used)
 {
     *used = false;
     static const bool enabled = []() { const char *e = getenv("BSFM_BA_CHOL_DATAFLOW"); return !(e && e[0] == '0'); }();
@@ -338,19 +342,32 @@ int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double 
     static const int grid_cap = []() { const char *e = getenv("BSFM_DF_GRID"); return e ? atoi(e) : 1 << 20; }();      // dev experiments
     const int grid = std::min(grid_cap, std::min(sm_count[dev].load(), 1 + std::max(1, ntile)));
     if (grid < 2 || ntile > 2 * (grid - 1)) return BSFM_OK;      // every worker keeps at most two tiles in registers
-    // workspace: [Z blocks nbk x 1024][back-substitution scratch n + 64][finished tiles (n + 1) x n]; the Z blocks and the tile
-    // area are pre-filled with the "not yet" pattern (all ones) by one memset
-    double *ywork = linv_ws + (size_t) nbk * LNB * LNB;
-    double *pub = ywork + n + 64;
-    BSFM_CUDA_TRY(cudaMemsetAsync(linv_ws, 0xFF, ((size_t) nbk * LNB * LNB + n + 64 + (size_t) (n + 1) * n) * sizeof(double), st));
-    int ld = n;
-    const double *Ac = A;
-    void *args[] = {&Ac, &Lmat, &ld, &n, &linv_ws, &pub, &sc};
+    // the Z blocks and the tile area are pre-filled with the "not yet" pattern (all ones): one memset when they are one range
+    const size_t zbytes = (size_t) nbk * LNB * LNB * sizeof(double), pbytes = (size_t) (n + 1) * n * sizeof(double);
+    const char *zb = reinterpret_cast<const char *>(linv_blocks), *pb = reinterpret_cast<const char *>(pub);
+    if (pb >= zb + zbytes && (size_t) (pb - zb) <= zbytes + (1u << 20)) {
+        BSFM_CUDA_TRY(cudaMemsetAsync(linv_blocks, 0xFF, (size_t) (pb - zb) + pbytes, st));
+    } else {
+        BSFM_CUDA_TRY(cudaMemsetAsync(linv_blocks, 0xFF, zbytes, st));
+        BSFM_CUDA_TRY(cudaMemsetAsync(pub, 0xFF, pbytes, st));
+    }
+    int ldp = n;
+    void *args[] = {&A, &Lmat, &ld, &n, &linv_blocks, &pub, &ldp, &sc};
     BSFM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *) chol_dataflow_kernel, dim3(grid), dim3(DF_THREADS), args, 0, st));
     count_launch();
-    chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, ld, n, linv_ws, x, ywork);
-    BSFM_KERNEL_CHECK();
     *used = true;
+    return BSFM_OK;
+}
+
+// small systems: factorisation + back substitution.  linv_ws: [Z blocks nbk x 1024][back-substitution scratch n + 64][(n + 1) x n]
+int chol_solve_dataflow(cudaStream_t st, double *A, double *Lmat, int n, double *linv_ws, double *x, Scalars *sc, bool *used)
+{
+    const int nbk = (n + LNB - 1) / LNB;
+    double *ywork = linv_ws + (size_t) nbk * LNB * LNB;
+    int rc = chol_dataflow_factor(st, A, Lmat, n, n, linv_ws, ywork + n + 64, sc, used);
+    if (rc != BSFM_OK || !*used) return rc;
+    chol_backsolve_blocked_kernel<<<1, 512, 0, st>>>(Lmat, n, n, linv_ws, x, ywork);
+    BSFM_KERNEL_CHECK();
     return BSFM_OK;
 }
 

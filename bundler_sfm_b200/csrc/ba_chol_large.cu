@@ -438,9 +438,23 @@ int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *li
     }
     const int sms = tc_sm_count();
     bool diag_done = false;       // diag(p) already issued by the look-ahead of panel p-1
+    // The last panels are latency-bound (a 110 us diagonal chain per panel that no trailing update hides any more): once the
+    // remaining matrix fits the one-launch dataflow factorisation (ba_chol_dataflow.cu, <= 640), it takes over in place -- same
+    // factor blocks, same 32 x 32 inverses, so the batched panel inverses and the back substitution below do not notice.
+    static const int tail_max = []() { const char *e = getenv("BSFM_BA_CHOL_TAIL"); return e ? atoi(e) : 640; }();
+    auto tail_fits = [&](int kk) { return kk > 0 && kk < n && n - kk <= tail_max && n - kk > 2 * LNB; };
     for (int k0 = 0; k0 < n; k0 += LNBO) {
         const int nb = std::min(LNBO, n - k0);
         const int k1 = k0 + nb;
+        if (!diag_done && tail_fits(k0)) {
+            bool used = false;
+            g_prof.begin(0, st);
+            int rc = chol_dataflow_factor(st, A + (size_t) k0 * ld + k0, Lmat + (size_t) k0 * ld + k0, ld, n - k0, linv_ws + (size_t) (k0 / LNB) * LNB * LNB,
+                                          linv_ws + chol_large_pub_offset(n), sc, &used);
+            g_prof.end(st);
+            if (rc != BSFM_OK) return rc;
+            if (used) break;
+        }
         if (!diag_done) {
             g_prof.begin(0, st);
             chol_diag_kernel<<<1, DG_THREADS, DG_SMEM_DOUBLES * sizeof(double), st>>>(A, Lmat, ld, n, k0, linv_ws, sc, k0 == 0 ? g_diag_dbg : nullptr);
@@ -466,7 +480,7 @@ int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *li
                 g_prof.fp64_flops += 2.0 * pairs * nb;
                 if (use_tc) g_prof.int8_ops += 2.0 * pairs * nb * (ws->ns * (ws->ns + 1) / 2);
             }
-            if (use_tc && lookahead) {
+            if (use_tc && lookahead && !tail_fits(k1)) {
                 const int col_tiles = LNBO / TC_TILE;      // the tile columns of the next panel
                 int rc = tc_syrk_update(st, *ws, A, Lmat, ld, nrows, k1, n, k0, k1, 0, col_tiles, 0);
                 if (rc != BSFM_OK) return rc;

@@ -12,6 +12,7 @@
 // chunk c of row r stored at chunk c ^ (r & 7)), so one cp.async.bulk brings a slice tile into shared memory ready
 // for tcgen05.mma -- the layout the MATCH descriptors use (match_kernels.cuh).
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cmath>
@@ -57,8 +58,12 @@ int chol_solve_large(cudaStream_t st, double *A, double *Lmat, int n, double *li
 constexpr int DF_MAX_N = 24 * LNB;       // largest system the dataflow path (ba_chol_dataflow.cu) takes: it needs (n + 1) x n doubles more
 inline size_t chol_extra_ws_doubles(int n)
 {
-    return (size_t) ((n + LNBO - 1) / LNBO) * LNBO * LNBO + (size_t) n + 64 + (n <= DF_MAX_N ? (size_t) (n + 1) * n + 64 : 0);
+    // small systems: (n + 1) x n behind the scratch; large ones finish their last panels with the dataflow kernel: room for its largest case
+    return (size_t) ((n + LNBO - 1) / LNBO) * LNBO * LNBO + (size_t) n + 64 + (size_t) (std::min(n, DF_MAX_N) + 1) * std::min(n, DF_MAX_N) + 64;
 }
+// where the large path keeps that scratch inside linv_ws
+inline size_t chol_large_pub_offset(int n) { return (size_t) ((n + LNB - 1) / LNB) * LNB * LNB + (size_t) ((n + LNBO - 1) / LNBO) * LNBO * LNBO + (size_t) n + 64; }
+int chol_dataflow_factor(cudaStream_t st, const double *A, double *Lmat, int ld, int n, double *linv_blocks, double *pub, Scalars *sc, bool *used);
 
 __host__ __device__ __forceinline__ size_t tc_slice_offset(int tile, int half, int k, int ns)
 {

@@ -277,6 +277,31 @@ def test_axb_chol_reports_indefinite_matrix(n):
     assert rc == 0
 
 
+def test_axb_chol_reports_indefinite_matrix_in_the_tail_of_a_large_system():
+    """the last panels of the 256-column path are finished by the dataflow kernel: a bad pivot there is reported as well"""
+    A = _spd(2000, seed=5)
+    A[1900, 1900] = -1.0
+    rc, _ = _axb_chol(A, np.ones(2000))
+    assert rc == 0
+
+
+def test_axb_chol_large_path_tail_hand_over_equals_panel_path():
+    """n = 2600: with and without the dataflow hand-over of the last panels (BSFM_BA_CHOL_TAIL=0), each in a child process"""
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from tests.test_ba_gpu import _spd, _axb_chol; "
+            "A = _spd(2600, 12); b = A @ np.random.default_rng(4).standard_normal(2600); rc, x = _axb_chol(A, b); "
+            "assert rc == 1; np.save(sys.argv[1], x)") % ROOT
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for tail in ("640", "0"):
+            f = os.path.join(td, f"x{tail}.npy")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, BSFM_BA_CHOL_TAIL=tail))
+            outs.append(np.load(f))
+    assert np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[1]) <= 1e-7
+
+
 @pytest.mark.parametrize("n", [97, 450, 640])
 def test_axb_chol_dataflow_equals_fused_step_path(n):
     """the cooperative dataflow factorisation (ba_chol_dataflow.cu) against the one-launch-per-32-columns path it replaces

@@ -597,12 +597,29 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// Operand staging of schur_partial_kernel.  Measured at config 3 (profiles/r2_ba3_sparse_kernels_before.csv): with the operands of
+// ONE tuple in flight per warp (register double buffer) the kernel ran at 1.56 TB/s with 41 % of the warp slots filled -- bound by
+// bytes in flight, not by HBM.  In-flight data now lives in shared memory: every warp keeps SCHUR_DEPTH tuples' operand blocks
+// (W_ij 27 + W_ik 27 + Vinv_i 9 + eb_i 3 doubles) on their way with cp.async (8-byte granules: the 216-byte W blocks are only
+// 8-byte aligned), and forms its MMA fragments from shared memory.  Same arithmetic, same order: bitwise the same partial sums.
+constexpr int SCHUR_DEPTH = 8;
+constexpr int SCHUR_STAGE = 68;          // doubles per staged tuple (66 used)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
 {
+    __shared__ double stage_all[4][SCHUR_DEPTH][SCHUR_STAGE];
+    __shared__ int4 rec_all[4][SCHUR_CHUNK];
     cudaGridDependencySynchronize();   // programmatic dependent launch (see launch_pdl)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= P.nchunks) return;
+    double (*stage)[SCHUR_STAGE] = stage_all[threadIdx.x >> 5];
     const int cnp = P.M.cnp, m = P.m;
     // block of this chunk: last b with chunk_off[b] <= c
     int lo = 0, hi = P.nblocks - 1;
@@ -623,34 +640,65 @@ __global__ void __launch_bounds__(128) schur_partial_kernel(Problem P)
     const double *eb = P.eab + (size_t) m * cnp;
     double a00[2] = {0, 0}, a01[2] = {0, 0}, a10[2] = {0, 0}, a11[2] = {0, 0};
 
-    // operands of tuple t+1 are in flight while tuple t is multiplied
-    double wa0[3] = {0, 0, 0}, wa1[3] = {0, 0, 0}, vi[3] = {0, 0, 0}, b0 = 0, b1 = 0;
-    auto load = [&](int t) {
-        const int4 tp = P.tuples[t];
-        const double *Wa = P.W + (size_t) tp.x * nY;
-        const double *Wb = P.W + (size_t) tp.y * nY;
-        const double *Vi = P.Vinv + (size_t) tp.z * 9;
-        if (kv) { vi[0] = Vi[tg]; vi[1] = Vi[3 + tg]; vi[2] = Vi[6 + tg]; }
-        if (r0v) { wa0[0] = Wa[g * 3]; wa0[1] = Wa[g * 3 + 1]; wa0[2] = Wa[g * 3 + 2]; }
-        if (r1v) { wa1[0] = Wa[(8 + g) * 3]; wa1[1] = Wa[(8 + g) * 3 + 1]; wa1[2] = Wa[(8 + g) * 3 + 2]; }
-        b0 = c0v ? Wb[g * 3 + tg] : 0.0;
-        b1 = c1v ? Wb[(8 + g) * 3 + tg] : (ev ? eb[(size_t) tp.z * 3 + tg] : 0.0);
+    // the chunk's tuple records (<= 64) go to shared memory once; every lane then knows, for each of its (at most three) 8-byte
+    // slots of a tuple's operand block, WHICH record component indexes it, the array it comes from and the stride -- all fixed
+    // for the whole chunk, so issuing a tuple is one shared-memory load, one multiply-add and one cp.async per slot
+    // (the first version selected among four pointers per element: 175 instructions per tuple, issue-bound at 2.0 ms;
+    // profiles/r2_schur_partial_v2.ncu.txt)
+    static_assert(SCHUR_CHUNK <= 64, "64 tuple records per warp");
+    int4 *recs = rec_all[threadIdx.x >> 5];
+    for (int q = lane; q < t1 - t0; q += 32) recs[q] = P.tuples[t0 + q];
+    // operand block layout: [0, nY) W_ij, [nY, 2 nY) W_ik, [2 nY, 2 nY + 9) Vinv_i, then eb_i (3)
+    const int oW2 = nY, oV = 2 * nY, oE = 2 * nY + 9, nElem = 2 * nY + 12;
+    const double *sbase[3];
+    int sstride[3], scomp[3];
+    bool sval[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const int e = lane + 32 * q;
+        sval[q] = e < nElem;
+        if (e < oW2)      { sbase[q] = P.W + e;             sstride[q] = nY; scomp[q] = 0; }
+        else if (e < oV)  { sbase[q] = P.W + (e - oW2);     sstride[q] = nY; scomp[q] = 1; }
+        else if (e < oE)  { sbase[q] = P.Vinv + (e - oV);   sstride[q] = 9;  scomp[q] = 2; }
+        else              { sbase[q] = eb + (e - oE);       sstride[q] = 3;  scomp[q] = 2; }
+    }
+    __syncwarp();
+    const int *reci = reinterpret_cast<const int *>(recs);
+    auto issue = [&](int i /* tuple index inside the chunk */) {
+        double *dst = stage[i % SCHUR_DEPTH] + lane;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            if (sval[q]) cp_async8(dst + 32 * q, sbase[q] + (size_t) reci[4 * i + scomp[q]] * sstride[q]);
     };
-    if (t0 < t1) load(t0);
-    for (int t = t0; t < t1; t++) {
+    const int nt = t1 - t0;
+    for (int d = 0; d < SCHUR_DEPTH; d++) {
+        if (d < nt) issue(d);
+        cp_async_commit();
+    }
+    for (int i = 0; i < nt; i++) {
+        cp_async_wait<SCHUR_DEPTH - 1>();            // this lane's part of tuple i has landed ...
+        __syncwarp();                               // ... and everybody else's
+        const double *S = stage[i % SCHUR_DEPTH];
+        double wa0[3] = {0, 0, 0}, wa1[3] = {0, 0, 0}, vi[3] = {0, 0, 0};
+        if (kv) { vi[0] = S[oV + tg]; vi[1] = S[oV + 3 + tg]; vi[2] = S[oV + 6 + tg]; }
+        if (r0v) { wa0[0] = S[g * 3]; wa0[1] = S[g * 3 + 1]; wa0[2] = S[g * 3 + 2]; }
+        if (r1v) { wa1[0] = S[(8 + g) * 3]; wa1[1] = S[(8 + g) * 3 + 1]; wa1[2] = S[(8 + g) * 3 + 2]; }
+        const double bb0 = c0v ? S[oW2 + g * 3 + tg] : 0.0;
+        const double bb1 = c1v ? S[oW2 + (8 + g) * 3 + tg] : (ev ? S[oE + tg] : 0.0);
         // Y[row][tg] = sum_c Wa[row][c] * Vinv[c][tg]   (sba_levmar.c:1206-1214)
         double y0 = 0.0, y1 = 0.0;
         y0 += wa0[0] * vi[0]; y0 += wa0[1] * vi[1]; y0 += wa0[2] * vi[2];
         y1 += wa1[0] * vi[0]; y1 += wa1[1] * vi[1]; y1 += wa1[2] * vi[2];
         if (!r0v) y0 = 0.0;
         if (!r1v) y1 = 0.0;
-        const double bb0 = b0, bb1 = b1;
-        if (t + 1 < t1) load(t + 1);
         // YWt += Y W_ik^T  (sba_levmar.c:1262-1275), E partial in column 9 (:1318-1333)
         dmma884(a00[0], a00[1], y0, bb0);
         dmma884(a01[0], a01[1], y0, bb1);
         dmma884(a10[0], a10[1], y1, bb0);
         dmma884(a11[0], a11[1], y1, bb1);
+        __syncwarp();                               // the stage is free again
+        if (i + SCHUR_DEPTH < nt) issue(i + SCHUR_DEPTH);
+        cp_async_commit();
     }
     // accumulator element (row = g, col = 2 tg + e) of tile (mt, nt) -> entry (mt*8 + g, nt*8 + 2 tg + e)
     double *out = P.schur_part + (size_t) c * SCHUR_PART_STRIDE;

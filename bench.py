@@ -412,7 +412,11 @@ def bench_ba(args, torch, dist, rank, world, dev, cfg_key, steps, warmup, scene=
         dev_s, e_s, its_all, e_its_all = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
     else:
         dev_s, e_s, its_all, e_its_all = t[0].item(), t[1].item(), t[2].item(), t[3].item()
-    h2d = n * m + nvis * 16 + m * ctypes.sizeof(bundle.CameraParams) + n * 24
+    # the dense n x m visibility mask of the reference interface is uploaded as it is, unless BSFM_BA_MASK_HOST_MIN enables the
+    # library's host-side compression (ba_solver.cu, host_scan_vmask: CRS, 4 (n + 1) + 4 nvis bytes; measured slower end to end here)
+    host_min = os.environ.get("BSFM_BA_MASK_HOST_MIN")
+    mask_bytes = (4 * (n + 1) + 4 * nvis) if (host_min is not None and n * m >= int(host_min)) else n * m
+    h2d = mask_bytes + nvis * 16 + m * ctypes.sizeof(bundle.CameraParams) + n * 24
     d2h = (m * cnp + 3 * n) * 8
     # algorithmic HBM bytes per LM iteration (SURVEY.md 8d / DESIGN.md): ~0.7 KB per observation + 16 (9m)^2
     alg_bytes = 0.7e3 * nvis + 16.0 * (9 * m) ** 2

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace bsfm {
@@ -60,6 +61,58 @@ __global__ void cam_ptr_kernel(const uint32_t *sorted_cam, int nvis, int m, int 
     }
     cam_ptr[j] = lo;
 }
+// obs_pt from the CRS row pointers (the host-scanned visibility mask below): one warp per point
+__global__ void csr_rows_kernel(const int *rowptr, int n, int *obs_pt)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    for (int q = rowptr[i] + lane; q < rowptr[i + 1]; q += 32) obs_pt[q] = i;
+}
+
+// The reference interface hands over a DENSE n x m visibility mask (sba.h: char *vmask): 500 MB at config 3 for 3M set bytes.
+// Large host-resident masks are compressed on the host instead of being uploaded: a few threads scan disjoint point ranges
+// (64 bytes per test, the mask is > 99 % zero) into the CRS form sba builds anyway (sba_levmar.c:652-663: row pointers per point,
+// camera index per observation, ascending), and only that travels: 4 (n + 1) + 4 nvis bytes.
+static void host_scan_vmask(const char *vmask, int n, int m, std::vector<int> &rowptr, std::vector<int> &obs_cam)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    const char *env = getenv("BSFM_BA_MASK_THREADS");
+    int T = env ? atoi(env) : (int) std::min(16u, std::max(1u, hw));
+    T = std::max(1, std::min(T, n));
+    std::vector<std::vector<int>> cams(T);
+    rowptr.assign((size_t) n + 1, 0);
+    auto work = [&](int t) {
+        const int i0 = (int) ((long long) n * t / T), i1 = (int) ((long long) n * (t + 1) / T);
+        std::vector<int> &out = cams[t];
+        for (int i = i0; i < i1; i++) {
+            const char *row = vmask + (size_t) i * m;
+            int cnt = 0, j = 0;
+            for (; j + 64 <= m; j += 64) {           // 64 bytes per branch: the mask is > 99 % zero
+                uint64_t w[8];
+                memcpy(w, row + j, 64);
+                if (!(w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7])) continue;
+                for (int u = 0; u < 64; u++)
+                    if (row[j + u]) { out.push_back(j + u); cnt++; }
+            }
+            for (; j < m; j++)
+                if (row[j]) { out.push_back(j); cnt++; }
+            rowptr[(size_t) i + 1] = cnt;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (int i = 0; i < n; i++) rowptr[(size_t) i + 1] += rowptr[i];
+    obs_cam.resize((size_t) rowptr[n]);
+    size_t pos = 0;
+    for (int t = 0; t < T; t++) {
+        if (!cams[t].empty()) memcpy(obs_cam.data() + pos, cams[t].data(), cams[t].size() * sizeof(int));
+        pos += cams[t].size();
+    }
+}
+
 __global__ void cast_u32_kernel(const int *in, uint32_t *out, int count)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,14 +308,20 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
 
     // ---------------- setup: vmask -> CRS (sba_levmar.c:652-663), camera-major permutation ----------------
     PT.begin(0);
-    char *d_vmask; int *d_rowcnt, *d_rowptr;
-    TRY(D.alloc(&d_vmask, (size_t) n * m));
+    char *d_vmask = nullptr; int *d_rowcnt, *d_rowptr;
+    // host-resident masks of at least BSFM_BA_MASK_HOST_MIN bytes are scanned on the host and only their CRS form is uploaded
+    // (host_scan_vmask above).  OFF by default: measured on the GPU box at config 3 (profiles/r2_hostmask_e2e.log) the threaded scan
+    // of the 500 MB mask costs more than its PCIe copy (H2D 560 -> 75 MB per solve, but e2e 62.6 -> 56-59 LM iterations/s).
+    static const size_t host_scan_min = []() { const char *e = getenv("BSFM_BA_MASK_HOST_MIN"); return e ? (size_t) atoll(e) : ~(size_t) 0; }();
+    bool host_mask = false;
+    if ((size_t) n * m >= host_scan_min) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, vmask) == cudaSuccess) host_mask = (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeUnregistered);
+        else cudaGetLastError();
+    }
+    std::vector<int> h_rowptr, h_obs_cam;
     TRY(D.alloc(&d_rowcnt, (size_t) n + 1));
     TRY(D.alloc(&d_rowptr, (size_t) n + 1));
-    BSFM_CUDA_TRY(cudaMemcpyAsync(d_vmask, vmask, (size_t) n * m, cudaMemcpyDefault, st));   // host or device pointer (UVA)
-    BSFM_CUDA_TRY(cudaMemsetAsync(d_rowcnt, 0, ((size_t) n + 1) * sizeof(int), st));
-    vmask_count_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_vmask, n, m, d_rowcnt);
-    BSFM_KERNEL_CHECK();
     size_t cub_bytes = 0;
     void *d_cub = nullptr;
     auto ensure_cub = [&](size_t need) -> int {
@@ -270,7 +329,15 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
         char *q; int rc = D.alloc(&q, need); if (rc != BSFM_OK) return rc;
         d_cub = q; cub_bytes = need; return BSFM_OK;
     };
-    {
+    if (host_mask) {
+        host_scan_vmask(vmask, n, m, h_rowptr, h_obs_cam);
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_rowptr, h_rowptr.data(), ((size_t) n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    } else {
+        TRY(D.alloc(&d_vmask, (size_t) n * m));
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_vmask, vmask, (size_t) n * m, cudaMemcpyDefault, st));   // host or device pointer (UVA)
+        BSFM_CUDA_TRY(cudaMemsetAsync(d_rowcnt, 0, ((size_t) n + 1) * sizeof(int), st));
+        vmask_count_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_vmask, n, m, d_rowcnt);
+        BSFM_KERNEL_CHECK();
         size_t need = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, need, d_rowcnt, d_rowptr, n + 1, st);
         TRY(ensure_cub(need));
@@ -278,8 +345,11 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
         count_launch(2);
     }
     int nvis = 0;
-    BSFM_CUDA_TRY(cudaMemcpyAsync(&nvis, d_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BSFM_CUDA_TRY(cudaStreamSynchronize(st));
+    if (host_mask) nvis = h_rowptr[n];
+    else {
+        BSFM_CUDA_TRY(cudaMemcpyAsync(&nvis, d_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BSFM_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     P.nvis = nvis;
     const int nobs = nvis * 2;
     if (nobs < P.nlm) {   // sba_levmar.c:647-650, :2235-2238
@@ -291,7 +361,12 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
     uint32_t *d_key_a, *d_key_b;
     TRY(D.alloc(&d_obs_cam, (size_t) nvis)); TRY(D.alloc(&d_obs_pt, (size_t) nvis));
     TRY(D.alloc(&d_cam_ptr, (size_t) m + 1)); TRY(D.alloc(&d_cam_obs, (size_t) nvis)); TRY(D.alloc(&d_iota, (size_t) nvis));
-    vmask_fill_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_vmask, n, m, d_rowptr, d_obs_cam, d_obs_pt);
+    if (host_mask) {
+        BSFM_CUDA_TRY(cudaMemcpyAsync(d_obs_cam, h_obs_cam.data(), (size_t) nvis * sizeof(int), cudaMemcpyHostToDevice, st));
+        csr_rows_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_rowptr, n, d_obs_pt);
+    } else {
+        vmask_fill_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_vmask, n, m, d_rowptr, d_obs_cam, d_obs_pt);
+    }
     BSFM_KERNEL_CHECK();
     double *d_x;
     TRY(D.alloc(&d_x, (size_t) nobs));

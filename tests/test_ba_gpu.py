@@ -302,6 +302,25 @@ def test_axb_chol_large_path_tail_hand_over_equals_panel_path():
     assert np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[1]) <= 1e-7
 
 
+def test_host_compressed_visibility_mask_equals_uploaded_mask():
+    """large host-resident masks are scanned on the host and uploaded as CRS (ba_solver.cu: host_scan_vmask); forced here on a
+    small scene (BSFM_BA_MASK_HOST_MIN=1, 3 scan threads) and compared bit for bit with the dense upload, in child processes"""
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from bundler_sfm_b200 import bundle, synth; "
+            "sc = synth.ba_scene(12, 3000, 5, seed=3); out = bundle.run_sfm(sc); "
+            "np.savez(sys.argv[1], info=out['info'], R=out['R'], c=out['c'], f=out['f'], k=out['k'], pts=out['pts'])") % ROOT
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for host_min in ("1", str(1 << 40)):
+            f = os.path.join(td, f"o{len(outs)}.npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, BSFM_BA_MASK_HOST_MIN=host_min, BSFM_BA_MASK_THREADS="3"))
+            outs.append(np.load(f))
+    for key in ("info", "R", "c", "f", "k", "pts"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+
+
 @pytest.mark.parametrize("n", [97, 450, 640])
 def test_axb_chol_dataflow_equals_fused_step_path(n):
     """the cooperative dataflow factorisation (ba_chol_dataflow.cu) against the one-launch-per-32-columns path it replaces

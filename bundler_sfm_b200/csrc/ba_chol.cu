@@ -13,8 +13,9 @@
 //                        outer panel gets one K = 256 SYRK-shaped update on the fp64 tensor cores
 //                        (mma.sync m8n8k4 f64, 128x128 tiles) -- the dense contraction of this path
 //   end                : chol_backsolve_blocked_kernel (1 CTA) L^T x = y with the inverted diagonal blocks
-// Small systems (<= 1536, e.g. 50 cameras -> 450) are one outer panel: latency-bound by the 450 sequential
-// pivots.  tcgen05 has no fp64 kind; an int8-slice (Ozaki) emulation of the trailing update is future work.
+// This file is the dispatcher (chol_solve) and the FUSED-STEP path for systems of 641..1536 (one outer panel: latency-bound by
+// the sequential pivots).  Systems <= 640 go to the one-launch dataflow factorisation (ba_chol_dataflow.cu), systems > 1536 to
+// the 256-column panel path with the tcgen05 int8-slice trailing update (ba_chol_large.cu, ba_chol_tc.cu).
 #include "ba_kernels.cuh"
 #include "ba_chol_large.cuh"
 #include "common.h"

@@ -70,48 +70,7 @@ __global__ void csr_rows_kernel(const int *rowptr, int n, int *obs_pt)
     for (int q = rowptr[i] + lane; q < rowptr[i + 1]; q += 32) obs_pt[q] = i;
 }
 
-// The reference interface hands over a DENSE n x m visibility mask (sba.h: char *vmask): 500 MB at config 3 for 3M set bytes.
-// Large host-resident masks are compressed on the host instead of being uploaded: a few threads scan disjoint point ranges
-// (64 bytes per test, the mask is > 99 % zero) into the CRS form sba builds anyway (sba_levmar.c:652-663: row pointers per point,
-// camera index per observation, ascending), and only that travels: 4 (n + 1) + 4 nvis bytes.
-static void host_scan_vmask(const char *vmask, int n, int m, std::vector<int> &rowptr, std::vector<int> &obs_cam)
-{
-    unsigned hw = std::thread::hardware_concurrency();
-    const char *env = getenv("BSFM_BA_MASK_THREADS");
-    int T = env ? atoi(env) : (int) std::min(16u, std::max(1u, hw));
-    T = std::max(1, std::min(T, n));
-    std::vector<std::vector<int>> cams(T);
-    rowptr.assign((size_t) n + 1, 0);
-    auto work = [&](int t) {
-        const int i0 = (int) ((long long) n * t / T), i1 = (int) ((long long) n * (t + 1) / T);
-        std::vector<int> &out = cams[t];
-        for (int i = i0; i < i1; i++) {
-            const char *row = vmask + (size_t) i * m;
-            int cnt = 0, j = 0;
-            for (; j + 64 <= m; j += 64) {           // 64 bytes per branch: the mask is > 99 % zero
-                uint64_t w[8];
-                memcpy(w, row + j, 64);
-                if (!(w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7])) continue;
-                for (int u = 0; u < 64; u++)
-                    if (row[j + u]) { out.push_back(j + u); cnt++; }
-            }
-            for (; j < m; j++)
-                if (row[j]) { out.push_back(j); cnt++; }
-            rowptr[(size_t) i + 1] = cnt;
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
-    for (int i = 0; i < n; i++) rowptr[(size_t) i + 1] += rowptr[i];
-    obs_cam.resize((size_t) rowptr[n]);
-    size_t pos = 0;
-    for (int t = 0; t < T; t++) {
-        if (!cams[t].empty()) memcpy(obs_cam.data() + pos, cams[t].data(), cams[t].size() * sizeof(int));
-        pos += cams[t].size();
-    }
-}
+// host_scan_vmask (common.cpp): dense n x m visibility mask -> CRS on the host, see there
 
 __global__ void cast_u32_kernel(const int *in, uint32_t *out, int count)
 {
@@ -330,7 +289,7 @@ static int levmar_impl(int mot, const double *fixed_pts, int n, int m, int mcon,
         d_cub = q; cub_bytes = need; return BSFM_OK;
     };
     if (host_mask) {
-        host_scan_vmask(vmask, n, m, h_rowptr, h_obs_cam);
+        bsfm::host_scan_vmask(vmask, n, m, h_rowptr, h_obs_cam);
         BSFM_CUDA_TRY(cudaMemcpyAsync(d_rowptr, h_rowptr.data(), ((size_t) n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     } else {
         TRY(D.alloc(&d_vmask, (size_t) n * m));

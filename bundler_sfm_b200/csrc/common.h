@@ -7,6 +7,7 @@
 #include <cstdio>
 #include "../../include/bsfm_b200.h"
 
+#include <vector>
 namespace bsfm {
 
 void set_error(const char *fmt, ...);
@@ -18,6 +19,8 @@ inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory
 // Fails loudly when no sm_100 device is usable.  Returns BSFM_OK or a negative error.
 int require_device();
 
+// dense n x m visibility mask (sba.h: char *vmask) -> CRS: rowptr[n + 1], obs_cam[nvis] ascending per point (common.cpp)
+void host_scan_vmask(const char *vmask, int n, int m, std::vector<int> &rowptr, std::vector<int> &obs_cam);
 }  // namespace bsfm
 
 #define BSFM_CUDA_TRY(expr)                                                                       \

@@ -1,19 +1,22 @@
-// ba_chol_dataflow.cu -- dense SPD factorisation of SMALL reduced camera systems (n <= 1536; config 2: 50 cameras -> 450)
-// as ONE co-resident launch per factorisation.  Reference: dpotrf inside sba_Axb_Chol, lib/sba-1.5/sba_lapack.c:429.
+// ba_chol_dataflow.cu -- dense SPD factorisation of SMALL reduced camera systems (n <= 640; config 2: 50 cameras -> 450) as ONE
+// co-resident launch per factorisation; also finishes the last panels of large systems in place (ba_chol_large.cu).
+// Reference: dpotrf inside sba_Axb_Chol, lib/sba-1.5/sba_lapack.c:429.
 //
-// Small systems are bound by the chain of n sequential pivots, not by FLOPs.  The fused-step path (ba_chol.cu) pays one
-// launch per 32 columns (15 for config 2) and a 16-warp, barrier-per-pivot factorisation of the diagonal tile in every CTA
-// (~600 cycles per pivot).  Here the whole factorisation is a dataflow over 32 x 32 tiles inside one cooperative launch:
-//   CTA 0        owns the critical path: for every 32-column step k it factors the diagonal tile (k,k) with ONE warp
-//                (8-column register panels + shuffles, ~230 cycles per pivot: warp_potf2_32), publishes L_kk, then itself
-//                applies step k to the NEXT diagonal tile (k+1,k+1) (solve of the sub-diagonal block + rank-32 update) and
-//                goes on to step k+1 -- look-ahead by construction.  A spare warp forms L_kk^-1 for the back substitution.
-//   CTAs 1..G-1  own the other tiles statically; for every step and owned tile they wait for L_kk and for the two panel
-//                blocks of their rows (per-tile version flags in global memory, acquire / release), solve them
-//                (thread per row), apply the rank-32 update, write the factor block if theirs is the first column, and
-//                publish the tile's version.  No grid-wide barrier anywhere.
-// Same data contract as chol_solve (factor OUT OF PLACE in Lmat, right-hand side as matrix row n).  Waits are bounded
-// (a lost flag sets sc->chol_fail = 2 instead of hanging the device).
+// Small systems are bound by the chain of n sequential pivots and by L2 round trips (~1 us each on B200), not by FLOPs.  The
+// fused-step path (ba_chol.cu) pays one launch per 32 columns and a 16-warp, barrier-per-pivot factorisation of the diagonal tile in
+// every CTA.  Here the whole factorisation is a dataflow over 32 x 32 tiles inside one cooperative launch, no grid-wide barrier:
+//   CTA 0        owns the critical path.  Per 32-column step k: warp 0 factors the diagonal tile (warp_potf2_32_tc, ba_chol_potf2.cuh),
+//                warp 1 assembles Z_kk = L_kk^-1 one panel behind it, warps 4..7 send Z_kk out the moment it exists, warps 2..3
+//                fetch the look-ahead inputs as they arrive; then X <- X Z^T for the sub-diagonal block and the rank-32 update
+//                of the NEXT diagonal tile, which never leaves shared memory.
+//   CTAs 1..G-1  own the other tiles statically (at most two each) and keep them in REGISTERS (DMMA accumulator layout) through
+//                all their rank-32 updates; a tile goes to global memory exactly once, when it is finished.  Per step: fetch the
+//                two finished panel blocks of every owned tile, then Z_kk, X <- X Z^T strips and the update on the fp64 tensor cores.
+//   transport    every 8-byte word that travels between CTAs is its own ready flag: it is written once into memory pre-filled
+//                with an all-ones pattern and re-read by the consumer until it differs (no flag round trip, no fence).
+// Same data contract as chol_solve (factor OUT OF PLACE in Lmat, right-hand side as matrix row n, inverses of the diagonal tiles in
+// linv).  Waits are bounded: a word that never arrives sets sc->chol_fail = 2 instead of hanging the device.
+// History and measurements: DESIGN.md 3.4, profiles/r2_chol_dataflow_v1..v4*.log (0.278 -> 0.142 ms at 450^2).
 #include "ba_kernels.cuh"
 #include "ba_chol_large.cuh"
 #include "ba_chol_potf2.cuh"

@@ -85,8 +85,10 @@ __device__ __forceinline__ int df_tile_index(int rb, int cb, int nbk)
     return before + (rb - cb);
 }
 
-// dev-only accounting of CTA 0 (read and reset by bsfm_debug_df_prof): [0] kernel ns, [1] potf2, [2] wait for the helpers' loads,
-// [3] sub-diagonal solve, [4] wait for the publish, [5] phase 3, [6] steps, [7] launches   ([1..5] in SM cycles)
+// dev-only accounting of CTA 0, thread 0 (read and reset by bsfm_debug_df_prof): [0] kernel ns, [1] potf2, [2] up to the barrier
+// behind inverse + loads, [3] X Z^T strips -- BAR.SYNC defers its blocking to the first dependent instruction, so the WAIT for the
+// look-ahead inputs shows up here --, [4] factor block out + update of the next diagonal tile, [5] end-of-step barrier, [6] steps,
+// [7] launches   ([1..5] in SM cycles)
 __device__ unsigned long long g_df_prof[8];
 __device__ __forceinline__ unsigned long long df_clock() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 __device__ __forceinline__ unsigned long long df_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }

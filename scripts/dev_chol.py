@@ -66,8 +66,8 @@ def main():
             dp = (ctypes.c_uint64 * 8)()
             if lib.bsfm_debug_df_prof(dp) == 0 and dp[7]:
                 v = list(dp); st = max(v[6], 1)
-                print(f"    dataflow CTA0: kernel {v[0]/v[7]/1e3:.1f} us/launch; cycles/step: potf2 {v[1]/st:.0f}  wait-loads {v[2]/st:.0f}  solve {v[3]/st:.0f}  "
-                      f"wait-publish {v[4]/st:.0f}  phase3 {v[5]/st:.0f}  ({v[6]} steps, {v[7]} launches)", flush=True)
+                print(f"    dataflow CTA0: kernel {v[0]/v[7]/1e3:.1f} us/launch; cycles/step: potf2 {v[1]/st:.0f}  barrier {v[2]/st:.0f}  strips+wait-for-inputs {v[3]/st:.0f}  "
+                      f"update {v[4]/st:.0f}  end-barrier {v[5]/st:.0f}  ({v[6]} steps, {v[7]} launches)", flush=True)
         if rc != 1:
             print(f"[{tag}] n={n}: rc={rc} err={lib.bsfm_last_error()}")
             continue
